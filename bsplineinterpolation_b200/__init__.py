@@ -1,0 +1,12 @@
+"""bsplineinterpolation_b200 -- B200 (sm_100a) implementation of the
+BSplineInterpolation hot path: batched spline evaluation and the separable
+control-point solve.  The numerical work lives in csrc/ (hand-written CUDA
+behind the C ABI of include/bspline_b200.h); this package is the thin host
+mirror of the reference API used by tests and benchmarks."""
+from ._capi import BsplError, lib  # noqa: F401
+from .interpolation import (BSpline, InterpolationFunction, InterpolationFunctionTemplate,  # noqa: F401
+                            band_solve, last_kernel_ms, launch_count, reset_launch_count,
+                            set_eval_path)
+
+__all__ = ["InterpolationFunction", "InterpolationFunctionTemplate", "BSpline", "band_solve", "lib",
+           "BsplError", "launch_count", "reset_launch_count", "last_kernel_ms", "set_eval_path"]

@@ -1,0 +1,152 @@
+// Device-side building blocks shared by the evaluation kernels: per-axis
+// parameters, uniform-knot reconstruction, knot-span location and Cox-de Boor
+// weights.  Everything that decides a span is written with explicit
+// round-to-nearest intrinsics (no FMA contraction) so that it reproduces the
+// reference's x86 arithmetic bit for bit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bspl {
+
+constexpr int kMaxDim = 3;
+constexpr int kMaxOrder = 5;
+
+// Per-axis description handed to kernels by value.
+template <typename R>
+struct AxisParams {
+    const R* t;      // knot array on the device, or nullptr on uniform axes
+    R lo, hi;        // user range [a, b]                       (uniform axes)
+    R dx;            // (b - a) / (n' - 1)                      Interpolation.hpp:335
+    R half_extra;    // 0.5 * extra, extra = knots - samples    Interpolation.hpp:338
+    R inv_dx;
+    R first, second; // range(): wrap interval of periodic axes BSpline.hpp:224-226
+    int n;           // control points
+    int K;           // knots
+    int periodic;
+    int pad_;
+    long long stride;  // element stride of this axis in the padded coefficient array
+};
+
+template <typename R> struct Arith;
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fmodr(double a, double b) { return fmod(a, b); }
+    static __device__ __forceinline__ double floorr(double a) { return floor(a); }
+};
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fmodr(float a, float b) { return fmodf(a, b); }
+    static __device__ __forceinline__ float floorr(float a) { return floorf(a); }
+};
+
+// Knot i of the axis.  Uniform axes rebuild the reference's value
+//   t[i] = a + (double(i) - 0.5*extra) * dx        (Interpolation.hpp:343-354)
+// with the clamped end knots of non-periodic axes set exactly (:340, :356-358).
+template <typename R, int O>
+__device__ __forceinline__ R knot_at(const AxisParams<R>& a, int i) {
+    if (a.t != nullptr) return a.t[i];
+    if (!a.periodic) {
+        if (i <= O) return a.lo;
+        if (i >= a.K - O - 1) return a.hi;
+    }
+    using A = Arith<R>;
+    return A::add(a.lo, A::mul(A::sub(static_cast<R>(i), a.half_extra), a.dx));
+}
+
+// get_knot_iter (BSpline.hpp:125-157).  Wraps x into [first, second) on periodic
+// axes (x is updated, as in the reference) and returns
+//   span = O + #{ i in [O+1, K-O-2] : t[i] <= x },
+// which is what both the hint-accept branch and the upper_bound branch of the
+// reference produce for strictly increasing interior knots.
+template <typename R, int O>
+__device__ __forceinline__ int locate(const AxisParams<R>& a, R& x) {
+    using A = Arith<R>;
+    if (a.periodic) {
+        const R period = A::sub(a.second, a.first);
+        const R x0 = x;
+        x = A::add(A::add(a.first, A::fmodr(A::sub(x0, a.first), period)),
+                   x0 < a.first ? period : R(0));
+    }
+    const int lo_i = O, hi_i = a.K - O - 2;
+    if (a.t == nullptr) {
+        // one multiply for the guess, then exact fix-up against the true knots
+        R g = A::floorr((x - a.lo) * a.inv_dx + a.half_extra);
+        g = fmax(g, static_cast<R>(lo_i));   // also maps NaN to lo_i
+        g = fmin(g, static_cast<R>(hi_i));
+        int s = static_cast<int>(g);
+        while (s < hi_i && knot_at<R, O>(a, s + 1) <= x) ++s;
+        while (s > lo_i && knot_at<R, O>(a, s) > x) --s;
+        return s;
+    }
+    // general knots: first index in [O+1, hi_i+1) with t > x, minus one
+    int lo = O + 1, hi = hi_i + 1;
+    while (lo < hi) {
+        const int mid = lo + ((hi - lo) >> 1);
+        if (!(x < a.t[mid])) lo = mid + 1; else hi = mid;
+    }
+    return lo - 1;
+}
+
+// Local knot window tk[m] = t[span - O + 1 + m], m = 0 .. 2O-1.
+template <typename R, int O>
+__device__ __forceinline__ void load_knot_window(const AxisParams<R>& a, int span, R* tk) {
+#pragma unroll
+    for (int m = 0; m < 2 * O; ++m) tk[m] = knot_at<R, O>(a, span - O + 1 + m);
+}
+
+// base_spline_value (BSpline.hpp:83-111): Cox-de Boor triangle of order `so`
+// (so <= O), result right-aligned in b[0..O].
+template <typename R, int O>
+__device__ __forceinline__ void basis_funs(const R* tk, R x, int so, R* b) {
+#pragma unroll
+    for (int i = 0; i <= O; ++i) b[i] = R(0);
+    b[O] = R(1);
+#pragma unroll
+    for (int i = 1; i <= O; ++i) {
+        if (i <= so) {
+            const int ib = O - i;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                const int l = O - 1 - (i - j);  // local index of t[span-(i-j)]
+                const int r = O + j;            // local index of t[span+j+1]
+                R left = R(0), right = R(0);
+                if (j != 0) left = b[ib + j] * (x - tk[l]) / (tk[r - 1] - tk[l]);
+                if (ib + j != O) right = b[ib + j + 1] * (tk[r] - x) / (tk[r] - tk[l + 1]);
+                b[ib + j] = left + right;
+            }
+        }
+    }
+}
+
+// Weights of the k-th derivative along one axis: w such that
+//   d^k/dx^k sum_j c[j] B_j(x) = sum_j w[j] c[j].
+// The reference differences the local control points k times
+// (BSpline.hpp:507-518: c[i] <- m (c[i]-c[i-1]) / (t[i-O+m] - t[i-O]), m = O..O-k+1)
+// and dots them with the order O-k basis; applying the transposed stages to
+// that basis gives the same number with the control points left untouched.
+template <typename R, int O>
+__device__ __forceinline__ void deriv_weights(const R* tk, R x, int k, R* w) {
+    basis_funs<R, O>(tk, x, O - k, w);
+#pragma unroll
+    for (int m = 1; m <= O; ++m) {
+        if (m > O - k) {
+#pragma unroll
+            for (int i = 0; i <= O; ++i) {
+                if (i >= O - m) {
+                    // a_i(m) = m / (t[span+i-O+m] - t[span+i-O]); local idx = global - (span-O+1)
+                    R v = R(0);
+                    if (i >= O + 1 - m) v = w[i] * (R(m) / (tk[i + m - 1] - tk[i - 1]));
+                    if (i + 1 <= O) v -= w[i + 1] * (R(m) / (tk[i + m] - tk[i]));
+                    w[i] = v;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bspl

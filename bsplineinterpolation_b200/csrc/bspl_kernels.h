@@ -1,0 +1,91 @@
+// Host-visible launch interface between the C-ABI layer (bspl_capi.cu) and the
+// kernel translation units.  Internal; the public surface is include/bspline_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bspl_device.cuh"
+
+namespace bspl {
+
+enum EvalMode { kValue = 0, kValueGrad = 1 };
+
+template <typename R>
+struct EvalArgs {
+    int dim, order;
+    AxisParams<R> ax[kMaxDim];
+    const R* coef;            // padded coefficient array of the first field to evaluate
+    long long field_stride;   // elements between consecutive fields
+    int n_fields;             // fields evaluated by this launch (out is [n_fields][q][n_out])
+    const R* pts;             // [q][dim]
+    R* out;
+    long long q;
+    int deriv[kMaxDim];       // kValue only
+    int mode;
+};
+
+// Direct gather: one query per thread straight from the padded global array.
+template <typename R>
+cudaError_t launch_eval_direct(const EvalArgs<R>& a, cudaStream_t s);
+
+// span - order per axis, int32 [q][dim]
+template <typename R>
+cudaError_t launch_locate(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s);
+
+// ---- control-point solve ----------------------------------------------------
+
+// Device-resident LU factors of one axis in row form (see bspl_solve.cu).
+template <typename R>
+struct AxisLU {
+    int n, p, q, cyclic;
+    const R* L;       // [n][p]  L(i, i-p+m)
+    const R* U;       // [n][q]  U(i, i+1+m)
+    const R* diag;    // [n]     U(i, i)
+    const R* bottom;  // [n][q]  side(n-q+r, j) at [j*q + r]          (cyclic)
+    const R* right;   // [n][p]  side(i, n-p+c) at [i*p + c]          (cyclic)
+    int bottom_len;   // entries j >= bottom_len are exactly zero
+    int right_len;    // entries i >= right_len are exactly zero (rows above the main band only)
+};
+
+// Geometry of one sweep over a (field, axis0, axis1, axis2) array: lines run
+// along `axis`, the remaining (up to three) dimensions enumerate the lines.
+struct SweepGeom {
+    int n;                   // line length
+    long long line_stride;   // element stride along the line
+    int m[3];                // sizes of the other dimensions, m[2] fastest
+    long long ms[3];         // their element strides
+};
+
+template <typename R>
+cudaError_t launch_sweep(const AxisLU<R>& lu, const SweepGeom& g, R* data, cudaStream_t s);
+
+// f (compact, [fields][n0][n1][n2]) -> padded coefficient array, rotating each
+// periodic axis by +shift[d] (InterpolationTemplate.hpp:451-462).
+struct CopyGeom {
+    int dim;
+    int n[kMaxDim];
+    int shift[kMaxDim];
+    long long dst_stride[kMaxDim];
+    long long src_field_stride, dst_field_stride;
+    long long fields;
+};
+template <typename R>
+cudaError_t launch_rotate_copy(const CopyGeom& g, const R* src, R* dst, cudaStream_t s);
+// fill the `ghost[d]` wrap-around cells of every periodic axis (cells n..n+ghost-1 := 0..ghost-1)
+struct GhostGeom {
+    int dim;
+    int n[kMaxDim];
+    int ghost[kMaxDim];
+    long long stride[kMaxDim];
+    long long field_stride;
+    long long fields;
+};
+template <typename R>
+cudaError_t launch_fill_ghosts(const GhostGeom& g, R* data, cudaStream_t s);
+// padded -> compact copy of one field (for control_points())
+template <typename R>
+cudaError_t launch_unpad_copy(const CopyGeom& g, const R* src_padded, R* dst_compact, cudaStream_t s);
+
+void count_launch(int n = 1);
+
+}  // namespace bspl

@@ -1,0 +1,327 @@
+"""Python mirror of the reference's user API for the hot path, over the C ABI.
+
+Names and argument meaning follow the reference headers:
+  InterpolationFunctionTemplate  <- InterpolationTemplate.hpp:32-581
+  InterpolationFunction          <- Interpolation.hpp:17-507
+  BSpline.from_knots             <- BSpline.hpp:188-210
+`<T, D, Order, U>` become run-time (dtype, len(shape), order).  numpy arrays play
+the role of intp::Mesh (row-major).  Host arrays (numpy) and device arrays (torch
+CUDA tensors) are both accepted for meshes, points and outputs; device arrays
+are used in place on the given stream.  Everything numeric happens in the CUDA
+library; this file only marshals pointers.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from ._capi import check, lib
+
+_NP = {_capi.F64: np.float64, _capi.F32: np.float32}
+
+
+def _dtype_code(dtype):
+    dt = np.dtype(dtype) if not isinstance(dtype, int) else None
+    if dt is None:
+        return dtype
+    if dt == np.float64:
+        return _capi.F64
+    if dt == np.float32:
+        return _capi.F32
+    raise TypeError("dtype must be float64 or float32")
+
+
+def _is_device(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _i64(v):
+    a = np.ascontiguousarray(v, dtype=np.int64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _i32(v):
+    a = np.ascontiguousarray(v, dtype=np.int32)
+    return a, a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _f64(v):
+    a = np.ascontiguousarray(v, dtype=np.float64)
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _split_ranges(dim, ranges):
+    """ranges[d] is (x_min, x_max) -> uniform axis, or a 1-D coordinate array ->
+    non-uniform axis (the value-pair / iterator-pair overloads of the reference)."""
+    if len(ranges) != dim:
+        raise ValueError("one range per dimension is required")
+    lo, hi, coords = [], [], []
+    for r in ranges:
+        arr = np.asarray(r, dtype=np.float64)
+        if arr.ndim == 1 and arr.size == 2 and isinstance(r, tuple):
+            lo.append(arr[0]); hi.append(arr[1]); coords.append(None)
+        elif arr.ndim == 1 and arr.size >= 2:
+            lo.append(arr[0]); hi.append(arr[-1]); coords.append(np.ascontiguousarray(arr))
+        else:
+            raise ValueError("range must be a (min, max) tuple or a coordinate array")
+    return lo, hi, coords
+
+
+class InterpolationFunction:
+    """Device-resident spline(s); one per field of the handle."""
+
+    def __init__(self, order=None, f=None, ranges=None, periodicity=None, dtype=np.float64, device=0,
+                 _handle=None):
+        self._h = None
+        if _handle is not None:
+            self._h = _handle
+        else:
+            f_arr = f if _is_device(f) else np.asarray(f)
+            shape = tuple(f_arr.shape)
+            tmpl = InterpolationFunctionTemplate(order, shape, ranges, periodicity, dtype=dtype, device=device)
+            self._h = tmpl.interpolate(f)._steal()
+        self._refresh()
+
+    # -- plumbing
+    def _steal(self):
+        h, self._h = self._h, None
+        return h
+
+    def _refresh(self):
+        L = lib()
+        dt, dim, order = C.c_int(), C.c_int(), C.c_int()
+        nf = C.c_int64()
+        n = (C.c_int64 * 3)()
+        per = (C.c_int * 3)()
+        uni = (C.c_int * 3)()
+        nk = (C.c_int64 * 3)()
+        lo = (C.c_double * 3)()
+        hi = (C.c_double * 3)()
+        check(L.bspl_function_info(self._h, dt, dim, order, nf, n, per, uni, nk, lo, hi))
+        self.dtype = _NP[dt.value]
+        self.dim, self.order, self.n_fields = dim.value, order.value, nf.value
+        self.shape = tuple(n[d] for d in range(self.dim))
+        self._periodic = [bool(per[d]) for d in range(self.dim)]
+        self._uniform = [bool(uni[d]) for d in range(self.dim)]
+        self._n_knots = [nk[d] for d in range(self.dim)]
+        self._range = [(lo[d], hi[d]) for d in range(self.dim)]
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bspl_function_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def copy(self):
+        out = C.c_void_p()
+        check(lib().bspl_function_clone(self._h, C.byref(out)))
+        return InterpolationFunction(_handle=out)
+
+    # -- properties (Interpolation.hpp:248-267)
+    def periodicity(self, d):
+        return self._periodic[d]
+
+    def uniform(self, d):
+        return self._uniform[d]
+
+    def range(self, d):
+        return self._range[d]
+
+    def get_order(self):
+        return self.order
+
+    def knots(self, d):
+        out = np.empty(self._n_knots[d])
+        check(lib().bspl_function_knots(self._h, d, out.ctypes.data_as(C.POINTER(C.c_double)), out.size))
+        return out
+
+    def control_points(self, field=0):
+        out = np.empty(self.shape, dtype=self.dtype)
+        check(lib().bspl_function_control_points(self._h, field, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- evaluation
+    def _marshal(self, points, out, n_out, fields=1, stream=None):
+        if _is_device(points):
+            import torch
+            pts = points.contiguous()
+            if pts.dtype != (torch.float64 if self.dtype == np.float64 else torch.float32):
+                raise TypeError("device points must have the spline's dtype")
+            q = pts.numel() // self.dim
+            shape = ((fields,) if fields > 1 else ()) + ((q, n_out) if n_out > 1 else (q,))
+            if out is None:
+                out = torch.empty(shape, dtype=pts.dtype, device=pts.device)
+            sp = stream if stream is not None else torch.cuda.current_stream(pts.device).cuda_stream
+            return pts, out, q, C.c_void_p(pts.data_ptr()), C.c_void_p(out.data_ptr()), 1, C.c_void_p(sp)
+        pts = np.ascontiguousarray(points, dtype=self.dtype).reshape(-1, self.dim)
+        q = pts.shape[0]
+        shape = ((fields,) if fields > 1 else ()) + ((q, n_out) if n_out > 1 else (q,))
+        if out is None:
+            out = np.empty(shape, dtype=self.dtype)
+        elif out.dtype != self.dtype or not out.flags.c_contiguous or out.size != int(np.prod(shape)):
+            raise ValueError("out must be a C-contiguous %s array of %s elements" % (self.dtype, shape))
+        return pts, out, q, pts.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 0, None
+
+    def evaluate(self, points, out=None, derivatives=None, field=0, stream=None):
+        """Batched operator() (derivatives=None) or derivative(coord, derivatives)."""
+        pts, out, q, pp, op, dev, sp = self._marshal(points, out, 1, stream=stream)
+        dv = None
+        if derivatives is not None:
+            if len(derivatives) != self.dim:
+                raise ValueError("one derivative order per dimension")
+            _keep, dv = _i32(derivatives)
+        check(lib().bspl_evaluate(self._h, field, pp, q, dv, op, dev, sp))
+        return out
+
+    def __call__(self, *coords):
+        """f(x, y, ...) with scalars, or f(points[q][dim])."""
+        if len(coords) == self.dim and all(np.isscalar(c) for c in coords):
+            return float(self.evaluate(np.asarray(coords, dtype=self.dtype)[None, :])[0])
+        (points,) = coords
+        return self.evaluate(points)
+
+    def at(self, points, field=0):
+        """operator() with the bounds check of Interpolation.hpp:153-169 (raises ValueError)."""
+        return self.derivative_at(points, None, field)
+
+    def derivative(self, points, derivatives, field=0):
+        return self.evaluate(points, derivatives=derivatives, field=field)
+
+    def derivative_at(self, points, derivatives, field=0):
+        pts, out, q, pp, op, dev, sp = self._marshal(np.asarray(points), None, 1)
+        dv = None
+        if derivatives is not None:
+            _keep, dv = _i32(derivatives)
+        bad = C.c_int64(-1)
+        check(lib().bspl_evaluate_at(self._h, field, pp, q, dv, op, C.byref(bad)))
+        return out
+
+    def value_grad(self, points, out=None, field=0, stream=None):
+        """Fused value + gradient: [q][1+dim]."""
+        pts, out, q, pp, op, dev, sp = self._marshal(points, out, self.dim + 1, stream=stream)
+        check(lib().bspl_evaluate_value_grad(self._h, field, pp, q, op, dev, sp))
+        return out
+
+    def evaluate_fields(self, points, out=None, stream=None):
+        """One query set on every field: [n_fields][q]."""
+        pts, out, q, pp, op, dev, sp = self._marshal(points, out, 1, fields=self.n_fields, stream=stream)
+        check(lib().bspl_evaluate_fields(self._h, pp, q, op, dev, sp))
+        return out.reshape(self.n_fields, q) if not _is_device(out) else out.view(self.n_fields, q)
+
+    def locate(self, points):
+        """span - order per axis (first control point index), int32 [q][dim]."""
+        pts = np.ascontiguousarray(points, dtype=self.dtype).reshape(-1, self.dim)
+        cell = np.empty(pts.shape, dtype=np.int32)
+        check(lib().bspl_locate(self._h, pts.ctypes.data_as(C.c_void_p), pts.shape[0],
+                                cell.ctypes.data_as(C.POINTER(C.c_int32)), 0, None))
+        return cell
+
+
+class InterpolationFunctionTemplate:
+    """Knots + factored collocation matrices of one mesh; interpolate() any number of fields."""
+
+    def __init__(self, order, shape, ranges, periodicity=None, dtype=np.float64, device=0):
+        self._h = None
+        shape = tuple(int(s) for s in (shape if np.ndim(shape) else (shape,)))
+        dim = len(shape)
+        if periodicity is None:
+            periodicity = [False] * dim
+        if np.ndim(periodicity) == 0:
+            periodicity = [bool(periodicity)] * dim
+        lo, hi, coords = _split_ranges(dim, ranges)
+        self.dim, self.order, self.shape = dim, int(order), shape
+        self.dtype = _NP[_dtype_code(dtype)]
+        self.device = device
+        _kn, n_p = _i64(shape)
+        _kp, per_p = _i32([int(bool(p)) for p in periodicity])
+        _kl, lo_p = _f64(lo)
+        _kh, hi_p = _f64(hi)
+        cp = (C.POINTER(C.c_double) * dim)()
+        for d in range(dim):
+            cp[d] = coords[d].ctypes.data_as(C.POINTER(C.c_double)) if coords[d] is not None else None
+        out = C.c_void_p()
+        check(lib().bspl_template_create(_dtype_code(dtype), dim, int(order), n_p, per_p, lo_p, hi_p, cp,
+                                         device, C.byref(out)))
+        self._h = out
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bspl_template_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def _mesh_ptr(self, f):
+        per = int(np.prod(self.shape))
+        if _is_device(f):
+            import torch
+            want = torch.float64 if self.dtype == np.float64 else torch.float32
+            if f.dtype != want or not f.is_contiguous():
+                raise TypeError("device mesh must be contiguous and of the template's dtype")
+            if f.numel() % per or tuple(f.shape[-self.dim:]) != self.shape:
+                raise ValueError("mesh shape %s does not match template %s" % (tuple(f.shape), self.shape))
+            sp = torch.cuda.current_stream(f.device).cuda_stream
+            return f, C.c_void_p(f.data_ptr()), f.numel() // per, 1, C.c_void_p(sp)
+        arr = np.ascontiguousarray(f, dtype=self.dtype)
+        if arr.size % per or tuple(arr.shape[-self.dim:]) != self.shape:
+            raise ValueError("mesh shape %s does not match template %s" % (arr.shape, self.shape))
+        return arr, arr.ctypes.data_as(C.c_void_p), arr.size // per, 0, None
+
+    def interpolate(self, f, into=None):
+        """interpolate(mesh) -> new function; interpolate(mesh, into=fn) reuses fn's storage.
+        A leading extra axis of `f` is a batch of fields."""
+        keep, ptr, n_fields, dev, sp = self._mesh_ptr(f)
+        if into is not None:
+            check(lib().bspl_template_interpolate_into(self._h, into._h, ptr, n_fields, dev, sp))
+            into._refresh()
+            return into
+        out = C.c_void_p()
+        check(lib().bspl_template_interpolate(self._h, ptr, n_fields, dev, sp, C.byref(out)))
+        return InterpolationFunction(_handle=out)
+
+
+class BSpline:
+    @staticmethod
+    def from_knots(order, periodicity, knots, control_points, dtype=np.float64, device=0):
+        """BSpline(periodicity, ctrl_pts, knot ranges...) -> evaluable function handle."""
+        ctrl = np.ascontiguousarray(control_points, dtype=_NP[_dtype_code(dtype)])
+        dim = ctrl.ndim
+        ks = [np.ascontiguousarray(k, dtype=np.float64) for k in knots]
+        kp = (C.POINTER(C.c_double) * dim)(*[k.ctypes.data_as(C.POINTER(C.c_double)) for k in ks])
+        _a, nk = _i64([len(k) for k in ks])
+        _b, nc = _i64(ctrl.shape)
+        _c, per = _i32([int(bool(p)) for p in periodicity])
+        out = C.c_void_p()
+        check(lib().bspl_function_from_control_points(_dtype_code(dtype), dim, int(order), nc, per, kp, nk,
+                                                      ctrl.ctypes.data_as(C.c_void_p), 1, device, C.byref(out)))
+        return InterpolationFunction(_handle=out)
+
+
+def band_solve(a, rhs, p, q, cyclic, device=0):
+    """BandLU factor + solve on the device (band-matrix-and-solver-test.cpp shape)."""
+    a_arr, a_p = _f64(a)
+    x = np.array(rhs, dtype=np.float64, copy=True, order="C")
+    n = a_arr.shape[0]
+    n_rhs = x.size // n
+    check(lib().bspl_band_solve(n, p, q, int(bool(cyclic)), a_p, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                n_rhs, device))
+    return x
+
+
+def launch_count():
+    return lib().bspl_launch_count()
+
+
+def reset_launch_count():
+    lib().bspl_reset_launch_count()
+
+
+def last_kernel_ms():
+    return lib().bspl_last_kernel_ms()
+
+
+def set_eval_path(path):
+    check(lib().bspl_set_eval_path({"auto": 0, "direct": 1, "binned": 2}.get(path, path)))

@@ -1,0 +1,167 @@
+/* bspline_b200 -- C ABI of the B200 (sm_100a) implementation of the
+ * BSplineInterpolation hot path: batched evaluation of
+ * intp::InterpolationFunction<T, D, Order, U> and the separable control-point
+ * solve that produces its coefficients.
+ *
+ * The reference (12ff54e/BSplineInterpolation, header-only C++) has no FFI;
+ * its boundary is the template API in src/include/Interpolation.hpp and
+ * src/include/InterpolationTemplate.hpp.  Each entry point below names the
+ * reference interface it stands in for (file:line in the reference checkout).
+ * <T, D, Order, U> are compile-time there and run-time here (dtype, dim,
+ * order); T == U (real scalars).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns a bspl_status and
+ *     records a message retrievable with bspl_last_error() (thread-local);
+ *   - meshes and control points are row-major, last index fastest
+ *     (Mesh.hpp:241-246); query points are [q][dim] (array of DimArray<coord>,
+ *     Interpolation.hpp:144);
+ *   - `on_device` != 0: pts/out/f are device pointers on the handle's device
+ *     and the work is enqueued on `stream` (a cudaStream_t, NULL = default
+ *     stream) without synchronising; == 0: host pointers, the call copies in,
+ *     runs, copies out and returns when the result is in `out`;
+ *   - there is NO CPU fallback: without a CUDA device every compute call
+ *     returns BSPL_ERR_CUDA.
+ */
+#ifndef BSPLINE_B200_H
+#define BSPLINE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSPL_MAX_DIM 3
+#define BSPL_MAX_ORDER 5
+
+typedef enum {
+    BSPL_OK = 0,
+    BSPL_ERR_INVALID = 1,     /* bad argument (INTP_ASSERT -> std::runtime_error, util.hpp:247-258) */
+    BSPL_ERR_CUDA = 2,        /* CUDA runtime failure / no device */
+    BSPL_ERR_DOMAIN = 3,      /* coordinate out of range (std::domain_error, Interpolation.hpp:482-491) */
+    BSPL_ERR_ALLOC = 4,       /* std::bad_alloc */
+    BSPL_ERR_UNSUPPORTED = 5  /* dim/order outside the instantiated set */
+} bspl_status;
+
+typedef enum { BSPL_F64 = 0, BSPL_F32 = 1 } bspl_dtype;
+
+/* InterpolationFunctionTemplate<T,D,O,U> (InterpolationTemplate.hpp:32-581):
+ * per-axis knot vectors and the LU factors of the collocation matrices, on
+ * the device, reusable for any number of fields on the same mesh. */
+typedef struct bspl_template bspl_template;
+
+/* InterpolationFunction<T,D,O,U> (Interpolation.hpp:17-507): knots plus the
+ * control points of n_fields >= 1 fields, device resident. */
+typedef struct bspl_function bspl_function;
+
+/* InterpolationFunctionTemplate ctor (InterpolationTemplate.hpp:60-79) ->
+ * create_knot_vector_ (Interpolation.hpp:322-362 uniform, :365-464
+ * non-uniform) + build_solver_ (InterpolationTemplate.hpp:254-446, BandLU
+ * factorisation BandLU.hpp:103-118 / :159-213).  n[d] = data points on axis d
+ * (INTP_PERIODIC_NO_DUMMY_POINT semantics: the closing sample of a periodic
+ * axis is implicit).  coords == NULL or coords[d] == NULL: uniform axis on
+ * [lo[d], hi[d]]; otherwise coords[d] holds n[d] (+1 if periodic) increasing
+ * abscissae.  device = CUDA ordinal. */
+int bspl_template_create(bspl_dtype dtype, int dim, int order, const int64_t* n,
+                         const int* periodic, const double* lo, const double* hi,
+                         const double* const* coords, int device, bspl_template** out);
+void bspl_template_destroy(bspl_template* t);
+
+/* interpolate(mesh) const& (InterpolationTemplate.hpp:118-125) ->
+ * solve_for_control_points_ (:448-580) for n_fields meshes stored back to back
+ * ([n_fields][n0]...[nD-1]); returns a new function. */
+int bspl_template_interpolate(const bspl_template* t, const void* f, int64_t n_fields,
+                              int on_device, void* stream, bspl_function** out);
+/* interpolate(function_type&, mesh) (InterpolationTemplate.hpp:136-143): reuse
+ * the storage of an existing function of the same template. */
+int bspl_template_interpolate_into(const bspl_template* t, bspl_function* fn, const void* f,
+                                   int64_t n_fields, int on_device, void* stream);
+
+/* BSpline(periodicity, ctrl_pts, knot_iter_pairs...) (BSpline.hpp:188-210): a
+ * spline straight from knot vectors and control points (host pointers).
+ * n_knots[d] - n_ctrl[d] must be order+1, or 2*order+1 on periodic axes. */
+int bspl_function_from_control_points(bspl_dtype dtype, int dim, int order,
+                                      const int64_t* n_ctrl, const int* periodic,
+                                      const double* const* knots, const int64_t* n_knots,
+                                      const void* ctrl, int64_t n_fields, int device,
+                                      bspl_function** out);
+/* copy constructor of InterpolationFunction (value semantics) */
+int bspl_function_clone(const bspl_function* fn, bspl_function** out);
+void bspl_function_destroy(bspl_function* fn);
+
+/* periodicity(d), uniform(d), range(d), knots_num(d), get_order()
+ * (Interpolation.hpp:248-267, BSpline.hpp:583-608).  Any out pointer may be
+ * NULL.  n/periodic/uniform/n_knots/range_lo/range_hi have dim entries. */
+int bspl_function_info(const bspl_function* fn, int* dtype, int* dim, int* order,
+                       int64_t* n_fields, int64_t* n, int* periodic, int* uniform,
+                       int64_t* n_knots, double* range_lo, double* range_hi);
+/* knots_begin(d)..knots_end(d) (BSpline.hpp:560-571), as double. */
+int bspl_function_knots(const bspl_function* fn, int axis, double* out, int64_t capacity);
+/* spline().control_points() in the plain (non-cell) layout (BSpline.hpp:575-577,
+ * :45-50): copies field `field` to host memory, row-major, dtype of the function. */
+int bspl_function_control_points(const bspl_function* fn, int64_t field, void* host_out);
+
+/* operator()(DimArray<coord>) (Interpolation.hpp:132-146) when deriv == NULL,
+ * derivative(coord, derivatives) (:177-205) otherwise (deriv has dim entries;
+ * any entry > order yields 0, BSpline.hpp:404-407).  No bounds check:
+ * out-of-range points extrapolate (non-periodic) or wrap (periodic).
+ * pts [q][dim] -> out [q]. */
+int bspl_evaluate(const bspl_function* fn, int64_t field, const void* pts, int64_t q,
+                  const int* deriv, void* out, int on_device, void* stream);
+/* at(coord) / derivative_at(coord, derivatives) (Interpolation.hpp:153-169,
+ * :213-244): as bspl_evaluate but returns BSPL_ERR_DOMAIN, with *first_bad =
+ * index of the first offending query, if a non-periodic coordinate lies outside
+ * range(d) (boundary_check_, :482-491).  Host pointers only. */
+int bspl_evaluate_at(const bspl_function* fn, int64_t field, const void* pts, int64_t q,
+                     const int* deriv, void* out, int64_t* first_bad);
+/* Fused value + gradient: out [q][1+dim] = {f, df/dx0, ..., df/dx(dim-1)}; what
+ * the reference obtains from one operator() and dim derivative() calls. */
+int bspl_evaluate_value_grad(const bspl_function* fn, int64_t field, const void* pts, int64_t q,
+                             void* out, int on_device, void* stream);
+/* One query set applied to every field (the device analogue of eval_proxy,
+ * InterpolationTemplate.hpp:145-176 / BSpline.hpp:244-297, following
+ * operator() where the two disagree): out [n_fields][q]. */
+int bspl_evaluate_fields(const bspl_function* fn, const void* pts, int64_t q, void* out,
+                         int on_device, void* stream);
+/* get_knot_iter (BSpline.hpp:125-157): cell[q][dim] = span - order per axis,
+ * exactly the first control-point index the reference selects. */
+int bspl_locate(const bspl_function* fn, const void* pts, int64_t q, int32_t* cell,
+                int on_device, void* stream);
+
+/* Raw banded solver, BandLU<BandMatrix>/<ExtendedBandMatrix> (BandLU.hpp): factor
+ * the dense row-major n x n matrix `a` (entries outside the band and the cyclic
+ * corners are ignored) and solve n_rhs right-hand sides [n_rhs][n] in place on
+ * the device.  Host pointers. */
+int bspl_band_solve(int64_t n, int64_t p, int64_t q, int cyclic, const double* a, double* x,
+                    int64_t n_rhs, int device);
+
+/* Host-only introspection of template construction (no device needed): the knot
+ * vector of one axis exactly as create_knot_vector_ builds it, and the factored
+ * collocation matrix in the row form the kernels consume.  factor arrays:
+ * L[n][P], U[n][P], diag[n] with P = *band (= max(p, q)); for periodic axes the
+ * corner strips bottom[n][P], right[n][P] (see bspl_kernels.h: AxisLU).  Pass NULL
+ * to query sizes only.  coords as in bspl_template_create (NULL = uniform). */
+int bspl_host_axis_knots(bspl_dtype dtype, int order, int periodic, int64_t n, double lo, double hi,
+                         const double* coords, double* knots_out, int64_t capacity,
+                         int64_t* n_knots, double* range_lo_hi);
+int bspl_host_axis_factor(bspl_dtype dtype, int order, int periodic, int64_t n, double lo, double hi,
+                          const double* coords, int* band, double* L, double* U, double* diag,
+                          double* bottom, double* right);
+
+/* Execution knobs.  path: 0 = auto, 1 = direct gather, 2 = cell-binned tiles. */
+int bspl_set_eval_path(int path);
+/* Number of kernels this library launched since the last reset (all threads). */
+int64_t bspl_launch_count(void);
+void bspl_reset_launch_count(void);
+/* Device time (ms) of the most recent host-pointer call's kernels only (CUDA
+ * events around the launches, excluding the copies); < 0 if none. */
+double bspl_last_kernel_ms(void);
+
+const char* bspl_last_error(void);
+const char* bspl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSPLINE_B200_H */

@@ -1,0 +1,108 @@
+"""CPU-only: the C-ABI library builds for sm_100a, loads, exports every symbol
+include/bspline_b200.h declares, and its host-side template construction (knots,
+collocation LU) equals the oracle bit for bit.  No kernels run here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle.pyoracle import OracleSpline
+
+dp = C.POINTER(C.c_double)
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bspline_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bspl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib_built):
+    from bsplineinterpolation_b200 import _capi
+    names = _declared_symbols()
+    assert len(names) >= 20
+    L = lib_built.lib()
+    for n in names:
+        assert hasattr(L, n), "missing export: " + n
+    assert set(names) == set(_capi.SIGNATURES), "python signatures out of sync with the header"
+    assert b"sm_100a" in L.bspl_version()
+
+
+def test_no_cpu_fallback_in_product():
+    """The product package must not import or link the oracle."""
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert "oracle" not in text.replace("no oracle", ""), fn
+
+
+def _host_knots(L, order, per, n, lo, hi, coords=None):
+    from bsplineinterpolation_b200._capi import check
+    nk = C.c_int64(); rng = (C.c_double * 2)()
+    cp = coords.ctypes.data_as(dp) if coords is not None else None
+    check(L.bspl_host_axis_knots(0, order, per, n, lo, hi, cp, None, 0, C.byref(nk), rng))
+    out = np.empty(nk.value)
+    check(L.bspl_host_axis_knots(0, order, per, n, lo, hi, cp, out.ctypes.data_as(dp), out.size, C.byref(nk), rng))
+    return out, (rng[0], rng[1])
+
+
+def _host_factor(L, order, per, n, lo, hi, coords=None):
+    from bsplineinterpolation_b200._capi import check
+    band = C.c_int()
+    cp = coords.ctypes.data_as(dp) if coords is not None else None
+    check(L.bspl_host_axis_factor(0, order, per, n, lo, hi, cp, C.byref(band), None, None, None, None, None))
+    P = band.value
+    arrs = [np.zeros((n, max(P, 1))) for _ in range(2)] + [np.zeros(n)] + [np.zeros((n, max(P, 1))) for _ in range(2)]
+    check(L.bspl_host_axis_factor(0, order, per, n, lo, hi, cp, C.byref(band), *[a.ctypes.data_as(dp) for a in arrs]))
+    return (P,) + tuple(arrs)
+
+
+@pytest.mark.parametrize("order", range(6))
+@pytest.mark.parametrize("per", [0, 1])
+def test_host_template_construction_matches_oracle(lib_built, order, per):
+    L = lib_built.lib()
+    rng = np.random.default_rng(order * 2 + per)
+    for n in (7, 12, 33, 64):
+        for nonuni in (0, 1):
+            if nonuni and order == 0 and not per:
+                continue
+            lo, hi = -1.3, 2.9
+            coords = None
+            if nonuni:
+                coords = np.sort(rng.uniform(lo, hi, n + per)); coords[0] = lo; coords[-1] = hi
+            o = OracleSpline(order, (n,), [per], lo=[lo], hi=[hi], coords=[coords] if nonuni else None)
+            k, r = _host_knots(L, order, per, n, lo, hi, coords)
+            assert np.array_equal(k, o.knots(0)) and r == o.range(0)
+            P, Lr, U, dg, B, R = _host_factor(L, order, per, n, lo, hi, coords)
+            band, right, bottom = o.lu(0)
+            p = band.shape[1] // 2
+            assert P == p
+            for i in range(n):
+                assert dg[i] == band[i, p]
+                for m in range(P):
+                    jl, ju = i - P + m, i + 1 + m
+                    if jl >= 0:
+                        assert Lr[i, m] == band[jl, i + p - jl]
+                    if ju < n:
+                        assert U[i, m] == band[ju, i + p - ju]
+            if per and P > 0:
+                for i in range(n):
+                    for j in range(n):
+                        if j > i + p and j >= n - p:
+                            assert R[i, j - (n - P)] == right[i, j + p - n]
+                        if i > j + p and i >= n - p:
+                            assert B[j, i - (n - P)] == bottom[j, i + p - n]
+
+
+def test_invalid_arguments_reported(lib_built):
+    from bsplineinterpolation_b200 import BsplError, InterpolationFunctionTemplate
+    with pytest.raises(BsplError) as e:
+        InterpolationFunctionTemplate(9, (8,), [(0.0, 1.0)])
+    assert e.value.code == 5  # BSPL_ERR_UNSUPPORTED
+    with pytest.raises(BsplError):
+        InterpolationFunctionTemplate(3, (8, 8, 8, 8), [(0.0, 1.0)] * 4)

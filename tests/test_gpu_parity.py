@@ -1,0 +1,249 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the oracle
+(and the reference's golden vectors) on identical inputs.
+
+Tolerances (BASELINE.json north_star): fp64 values / derivatives / control points
+<= 1e-12 relative (reference rel_err metric AND max-abs vs field scale); span and
+index selection bit-exact.  Control points are in fact expected to be bit-identical
+(same elimination order, unfused arithmetic)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from cases import adversarial_points, all_combos, axis_ranges, queries, small_shapes, smooth_field
+from oracle.pyoracle import OracleSpline
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _close(a, b, tol=TOL):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-300)
+    assert np.abs(a - b).max() <= tol * scale, (np.abs(a - b).max(), scale)
+    if np.abs(b).sum() > 0:
+        assert rel_err(a, b) <= tol
+
+
+@pytest.fixture(scope="module")
+def pkg(lib_built):
+    return lib_built
+
+
+def _ranges(lo, hi):
+    return [(float(a), float(b)) for a, b in zip(lo, hi)]
+
+
+@pytest.mark.parametrize("dim,order,periodic", list(all_combos()))
+def test_solve_and_eval_match_oracle(pkg, dim, order, periodic):
+    rng = np.random.default_rng(1000 * dim + 10 * order + sum(periodic))
+    shape = small_shapes(dim, order, periodic)
+    lo, hi = axis_ranges(dim, rng)
+    f = smooth_field(shape, rng)
+    o = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=f)
+    fn = pkg.InterpolationFunction(order, f, _ranges(lo, hi), periodic)
+    for d in range(dim):
+        assert np.array_equal(fn.knots(d), o.knots(d))
+        assert fn.range(d) == o.range(d)
+        assert fn.periodicity(d) == bool(periodic[d]) and fn.uniform(d)
+    ctrl = fn.control_points()
+    assert np.array_equal(ctrl, o.control_points()), np.abs(ctrl - o.control_points()).max()
+
+    rlo = np.array([o.range(d)[0] for d in range(dim)]); rhi = np.array([o.range(d)[1] for d in range(dim)])
+    adv = adversarial_points([o.knots(d) for d in range(dim)], rlo, rhi, periodic, rng)
+    assert np.array_equal(fn.locate(adv), o.spans(adv))
+    wild = queries(rlo, rhi, periodic, 4000, rng, mode="wild")
+    assert np.array_equal(fn.locate(wild), o.spans(wild))
+
+    pts = queries(rlo, rhi, periodic, 3000, rng)
+    _close(fn(pts), o.eval(pts))
+    _close(fn(wild), o.eval(wild), 1e-10)  # extrapolation amplifies rounding
+    for dv in ([1] + [0] * (dim - 1), [min(order, 2)] * dim, [0] * (dim - 1) + [order]):
+        _close(fn.derivative(pts, dv), o.deriv(pts, dv))
+    assert not fn.derivative(pts, [order + 1] + [0] * (dim - 1)).any()  # BSpline.hpp:404-407
+    vg = fn.value_grad(pts)
+    _close(vg[:, 0], o.eval(pts))
+    for d in range(dim):
+        dv = [0] * dim; dv[d] = 1
+        _close(vg[:, 1 + d], o.deriv(pts, dv))
+
+
+def test_reference_golden_vectors(pkg, golden):
+    """Every known-answer vector of interpolation-test.cpp that is on the path (tol 1e-14, :16)."""
+    g = golden["interpolation"]
+    tol = 1e-14
+    IF = pkg.InterpolationFunction
+    f = np.array(g["f"])
+    xs_h = np.array(g["coords_1d_half"]); xs = np.array(g["coords_1d"])
+    cubic = IF(3, f, [(0.0, 6.0)])
+    assert rel_err(cubic(xs_h), g["vals_1d"]) < tol
+    assert rel_err(cubic.derivative_at(xs_h, [1]), g["vals_1d_derivative_1"]) < tol
+    assert abs(cubic(-0.5) - g["extrapolate_left"][1]) < tol
+    assert abs(cubic(6.5) - g["extrapolate_right"][1]) < tol
+    idx = np.floor(xs).astype(int)
+    assert rel_err(IF(1, f, [(0.0, 12.0)])(xs), f[idx] + (f[idx + 1] - f[idx]) * (xs - idx)) < tol
+    assert rel_err(IF(0, f, [(0.0, 12.0)])(xs), f[np.round(xs).astype(int)]) < tol
+    fp = f[:-1]
+    quart = IF(4, fp, [(0.0, 12.0)], [True])
+    assert rel_err(quart(xs), g["vals_1d_periodic"]) < tol
+    assert rel_err(quart.derivative_at(xs, [1]), g["vals_1d_derivative_periodic"]) < tol
+    assert abs(quart(xs[0] - 12) - g["vals_1d_periodic"][0]) < tol
+    assert abs(quart(xs[0] + 12) - g["vals_1d_periodic"][0]) < tol
+    assert rel_err(IF(1, fp, [(0.0, 12.0)], [True])(xs), fp[idx] + (fp[(idx + 1) % 12] - fp[idx]) * (xs - idx)) < tol
+    f2 = np.array(g["f2"]).reshape(5, 5); c2 = np.array(g["coords_2d"]).reshape(-1, 2)
+    s2 = IF(3, f2, [(0.0, 4.0), (0.0, 4.0)])
+    assert s2.uniform(0) and s2.uniform(1)
+    assert rel_err(s2(c2), g["vals_2d"]) < tol
+    assert rel_err(s2.derivative_at(c2, [2, 1]), g["vals_2d_derivative_x2_y1"]) < tol
+    with pytest.raises(ValueError):  # std::domain_error, :159-164
+        s2.at(np.array([[-1.0, 1.0]]))
+    assert rel_err(IF(3, f2[:, :4], [(0.0, 4.0), (0.0, 4.0)], [False, True])(c2), g["vals_2d_periodic"]) < tol
+    f3 = np.array(g["f3"]).reshape(5, 6, 7); c3 = np.array(g["coords_3d"]).reshape(-1, 3)
+    s3 = IF(3, f3, [(0.0, 4.0), (0.0, 5.0), (0.0, 6.0)])
+    assert rel_err(s3(c3), g["vals_3d"]) < tol
+    assert rel_err(s3.derivative_at(c3, [1, 0, 3]), g["vals_3d_derivative_x1_y0_z3"]) < tol
+    assert not any(s3.periodicity(d) for d in range(3))
+    # non-uniform axes (:517-670)
+    xc = np.array(g["input_coords_1d"])
+    assert rel_err(IF(3, f, [xc])(xs), g["vals_1d_nonuniform"]) < tol
+    nup = IF(4, fp, [xc], [True])
+    assert not nup.uniform(0)
+    assert rel_err(nup(xs), g["vals_1d_nonuniform_periodic"]) < tol
+    mixed = IF(3, f2[:4], [(0.0, 4.0), np.array(g["nonuniform_coord_for_2d"])], [True, False])
+    assert rel_err(mixed(c2), g["vals_2d_X_periodic_Y_nonuniform"]) < tol
+
+
+def test_bspline_golden_vectors(pkg, golden):
+    """bspline-test.cpp: spline from knots + control points (tol 1e-15, :45)."""
+    b = golden["bspline"]
+    tol = 2e-15
+    k = b["knots"]
+    s1 = pkg.BSpline.from_knots(3, [0], [k], np.array(b["cp"]))
+    x1 = np.array(b["coords_1d"])
+    assert rel_err(s1(x1), b["vals_1d"]) < tol
+    assert rel_err(s1.derivative(x1, [0]), b["vals_1d"]) < tol
+    assert rel_err(s1.derivative(x1, [1]), b["vals_1d_derivative_1"]) < tol
+    assert rel_err(s1.derivative(x1, [2]), b["vals_1d_derivative_2"]) < tol
+    cp2 = np.array(b["cp2"]).reshape(5, 5); x2 = np.array(b["coords_2d"]).reshape(-1, 2)
+    s2 = pkg.BSpline.from_knots(3, [0, 0], [k, k], cp2)
+    assert rel_err(s2(x2), b["vals_2d"]) < tol
+    assert rel_err(s2.derivative(x2, [2, 0]), b["vals_2d_derivative_x2_y0"]) < tol
+    assert rel_err(s2.derivative(x2, [1, 1]), b["vals_2d_derivative_x1_y1"]) < tol
+    s2p = pkg.BSpline.from_knots(3, [0, 1], [k, b["knots2"]], cp2)
+    assert rel_err(s2p(x2), b["vals_2d_periodic"]) < tol
+    assert rel_err(s2p.derivative(x2, [1, 1]), b["vals_2d_periodic_derivative_x1_y1"]) < tol
+    cp3 = np.array(b["cp3"]).reshape(5, 5, 5); x3 = np.array(b["coords_3d"]).reshape(-1, 3)
+    s3 = pkg.BSpline.from_knots(3, [0, 0, 0], [k, k, k], cp3)
+    assert rel_err(s3(x3), b["vals_3d"]) < tol
+
+
+def test_committed_reference_outputs(pkg):
+    """Outputs of the unmodified reference (tests/golden/ref_outputs.npz)."""
+    import os
+    from conftest import ROOT
+    data = np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs.npz"))
+    for c in range(int(data["n_cases"])):
+        order = int(data["c%d_order" % c]); per = [bool(v) for v in data["c%d_periodic" % c]]
+        f = data["c%d_f" % c]
+        fn = pkg.InterpolationFunction(order, f, _ranges(data["c%d_lo" % c], data["c%d_hi" % c]), per)
+        assert np.array_equal(fn.control_points(), data["c%d_ctrl" % c])
+        pts = data["c%d_pts" % c]
+        assert np.array_equal(fn.locate(pts), data["c%d_spans" % c])
+        _close(fn(pts), data["c%d_vals" % c], 1e-10)  # includes extrapolated points
+        _close(fn.derivative(pts, [int(v) for v in data["c%d_dv" % c]]), data["c%d_dvals" % c], 1e-9)
+
+
+def test_band_solver(pkg):
+    """band-matrix-and-solver-test.cpp: ||b - A x|| / ||b|| < 1e-10, and bit parity with the oracle."""
+    from test_oracle import _band_matrices
+    from oracle.pyoracle import port_band_solve
+    n = 64
+    rhs = np.random.default_rng(5).uniform(-1, 1, (3, n))
+    for a, p, q, cyc in _band_matrices(n):
+        x = pkg.band_solve(a, rhs, p, q, cyc)
+        for r in range(3):
+            assert np.linalg.norm(a @ x[r] - rhs[r]) / np.linalg.norm(rhs[r]) < 1e-10
+            assert np.array_equal(x[r], port_band_solve(a, rhs[r], p, q, cyc))
+
+
+def test_nonuniform_axes_match_oracle(pkg):
+    rng = np.random.default_rng(77)
+    for order in range(1, 6):
+        for per in (False, True):
+            n = 29
+            xc = np.sort(rng.uniform(0, 5, n + per)); xc[0] = 0; xc[-1] = 5
+            f = rng.standard_normal(n)
+            o = OracleSpline(order, (n,), [per], coords=[xc], f=f)
+            fn = pkg.InterpolationFunction(order, f, [xc], [per])
+            assert np.array_equal(fn.knots(0), o.knots(0))
+            assert np.array_equal(fn.control_points(), o.control_points())
+            pts = rng.uniform(0, 5, 2000)
+            assert np.array_equal(fn.locate(pts)[:, 0], o.spans(pts)[:, 0])
+            _close(fn(pts), o.eval(pts))
+            _close(fn.derivative(pts, [1]), o.deriv(pts, [1]))
+
+
+def test_template_reuse_many_fields(pkg):
+    """InterpolationFunctionTemplate: one mesh, many fields (cfg5 shape, scaled down)."""
+    rng = np.random.default_rng(3)
+    shape = (32, 24)
+    F = 7
+    fields = np.stack([smooth_field(shape, rng) for _ in range(F)])
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0), (-1.0, 1.0)], [True, False])
+    fn = t.interpolate(fields)
+    assert fn.n_fields == F
+    pts = queries(np.array([0.0, -1.0]), np.array([1.0, 1.0]), [True, False], 1500, rng)
+    allv = fn.evaluate_fields(pts)
+    for k in range(F):
+        o = OracleSpline(3, shape, [True, False], lo=[0, -1], hi=[1, 1], f=fields[k])
+        assert np.array_equal(fn.control_points(k), o.control_points())
+        _close(allv[k], o.eval(pts))
+        _close(fn.evaluate(pts, field=k), o.eval(pts))
+    # interpolate(fn, mesh): reuse storage
+    again = t.interpolate(fields[::-1].copy(), into=fn)
+    assert np.array_equal(again.control_points(0), OracleSpline(3, shape, [True, False], lo=[0, -1], hi=[1, 1],
+                                                                 f=fields[-1]).control_points())
+    cp = fn.copy()
+    assert np.array_equal(cp.control_points(2), fn.control_points(2))
+
+
+def test_device_pointer_entry_points(pkg):
+    import torch
+    rng = np.random.default_rng(11)
+    shape = (40, 36, 28)
+    f = smooth_field(shape, rng)
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 3)
+    fn = t.interpolate(torch.from_numpy(f).cuda())
+    o = OracleSpline(3, shape, [0, 0, 0], lo=[0, 0, 0], hi=[1, 1, 1], f=f)
+    assert np.array_equal(fn.control_points(), o.control_points())
+    pts = rng.uniform(0, 1, (5000, 3))
+    dv = fn.value_grad(torch.from_numpy(pts).cuda())
+    torch.cuda.synchronize()
+    vg = dv.cpu().numpy()
+    _close(vg[:, 0], o.eval(pts))
+    _close(vg[:, 2], o.deriv(pts, [0, 1, 0]))
+
+
+def test_empty_and_single_queries(pkg):
+    f = np.arange(10.0)
+    fn = pkg.InterpolationFunction(3, f, [(0.0, 9.0)])
+    assert fn(np.empty((0, 1))).shape == (0,)
+    assert abs(fn(4.0) - 4.0) < 1e-12  # cubic spline reproduces a linear function
+    assert abs(fn.derivative(np.array([[2.5]]), [1])[0] - 1.0) < 1e-12
+
+
+def test_medium_3d_properties(pkg):
+    """Size-independent checks at a larger size: the interpolant reproduces its data at
+    the mesh nodes, and solve is linear."""
+    rng = np.random.default_rng(21)
+    shape = (96, 80, 72)
+    f1 = smooth_field(shape, rng); f2 = smooth_field(shape, rng)
+    rngs = [(0.0, 1.0), (0.0, 2.0), (-1.0, 1.0)]
+    t = pkg.InterpolationFunctionTemplate(3, shape, rngs, [False, True, False])
+    fn = t.interpolate(np.stack([f1, f2, 2.0 * f1 - 3.0 * f2]))
+    c = [fn.control_points(k) for k in range(3)]
+    assert np.abs(c[2] - (2.0 * c[0] - 3.0 * c[1])).max() <= 1e-12 * np.abs(c[2]).max()
+    ax0 = np.linspace(0, 1, shape[0]); ax1 = np.arange(shape[1]) * (2.0 / shape[1]); ax2 = np.linspace(-1, 1, shape[2])
+    idx = rng.integers(0, [shape[0], shape[1], shape[2]], size=(4000, 3))
+    nodes = np.stack([ax0[idx[:, 0]], ax1[idx[:, 1]], ax2[idx[:, 2]]], axis=1)
+    vals = fn.evaluate(nodes, field=0)
+    assert np.abs(vals - f1[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f1).max()
