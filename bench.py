@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""Headline benchmark: 3-D cubic fp64 value+gradient evaluation on a 256^3 mesh
+(BASELINE.json configs[2]), one process per GPU, queries sharded across ranks with
+replicated coefficients and no collective on the data path (weak scaling: every
+rank evaluates Q_PER_GPU queries per step).  Also reports the second half of the
+metric, the 512^3 control-point solve time, under "solve".
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One JSON line on stdout (rank 0).  `--impl reference` times the reference's own
+CPU implementation (oracle/_ref, the unmodified headers compiled by
+oracle/Makefile; falls back to the C port when that build is absent) on the
+host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MESH = (256, 256, 256)
+ORDER = 3
+Q_PER_GPU = 1 << 28          # queries per rank per step (BASELINE configs[2]: 256M)
+CPU_SAMPLE = 1 << 21         # queries timed on the CPU (value + 3 derivative calls each)
+B_QUERY = 8 * 3 + 8 * 4 + 8 * 64   # algorithmic bytes per query, SURVEY 8(d): coords + out + stencil
+B_STREAM = 8 * 3 + 8 * 4           # streamed bytes only
+SOLVE_MESH = (512, 512, 512)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def smooth_field_np(shape):
+    """prod_d cos(2 pi i_d / N_d - pi)  (interpolation-speed-test.cpp:84-89)"""
+    f = np.ones(shape)
+    for d, n in enumerate(shape):
+        ax = np.cos(2 * np.pi * np.arange(n) / n - np.pi)
+        f = f * ax.reshape([-1 if e == d else 1 for e in range(len(shape))])
+    return f
+
+
+# ----------------------------------------------------------------------------- reference arm
+class CpuReference:
+    """value + gradient through the reference: one operator() and three derivative() calls
+    per point (the reference has no fused gradient), split over all host threads."""
+
+    def __init__(self, threads):
+        from oracle import pyoracle
+        pyoracle.build()
+        self.threads = threads
+        f = smooth_field_np(MESH)
+        t0 = time.perf_counter()
+        if pyoracle.ref_available():
+            self.sp = pyoracle.RefSpline(ORDER, f, [0, 0, 0], lo=[0, 0, 0], hi=[1, 1, 1], kind="cell")
+            self.kind = "reference"
+        else:
+            self.sp = pyoracle.OracleSpline(ORDER, MESH, [0, 0, 0], lo=[0, 0, 0], hi=[1, 1, 1], f=f,
+                                            nthreads=threads)
+            self.kind = "port"
+        self.construct_s = time.perf_counter() - t0
+        self.pts = np.random.default_rng(12345).uniform(0.0, 1.0, (CPU_SAMPLE, 3))
+
+    def step(self, n=None):
+        pts = self.pts if n is None else self.pts[:n]
+        t0 = time.perf_counter()
+        self.sp.eval(pts, self.threads)
+        for dv in ([1, 0, 0], [0, 1, 0], [0, 0, 1]):
+            self.sp.deriv(pts, dv, self.threads)
+        return time.perf_counter() - t0
+
+    def describe(self, dt):
+        return ("%d uniform-random queries per step, operator() + 3 derivative() calls each, std::thread "
+                "split over %d threads (%.2f s per step; construct %.1f s not timed)"
+                % (CPU_SAMPLE, self.threads, dt, self.construct_s))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    ref = CpuReference(threads)
+    for _ in range(min(args.warmup, 2)):
+        ref.step(CPU_SAMPLE // 8)
+    total = sum(ref.step() for _ in range(args.steps))
+    value = CPU_SAMPLE * args.steps / total / 1e6
+    line = {
+        "impl": "reference", "metric": "3D cubic fp64 value+gradient eval", "value": value, "unit": "Mpts/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: 3D cubic 256^3 mesh, value+gradient; CPU step = %d-query sample" % CPU_SAMPLE,
+                   "mesh": list(MESH), "order": ORDER},
+        "cpu_baseline": {"value": value, "unit": "Mpts/s", "cores": threads, "kind": ref.kind,
+                         "sample": ref.describe(total / args.steps)},
+        "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.tmp.flush()
+        rows = [r.strip().split(", ") for r in open(self.tmp.name) if r.strip()]
+        os.unlink(self.tmp.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import bsplineinterpolation_b200 as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_kind = peaks()
+    q = args.queries
+    # replicated coefficients: every rank solves the same 256^3 field (outside the timed region)
+    tmpl = B.InterpolationFunctionTemplate(ORDER, MESH, [(0.0, 1.0)] * 3, device=local)
+    f = torch.from_numpy(smooth_field_np(MESH)).to(dev)
+    fn = tmpl.interpolate(f)
+    del f
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(12345 + rank)
+    pts = torch.rand((q, 3), dtype=torch.float64, device=dev, generator=gen)
+    out = torch.empty((q, 4), dtype=torch.float64, device=dev)
+
+    def step():
+        fn.value_grad(pts, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    B.reset_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        ev[k][0].record()
+        step()
+        ev[k][1].record()
+    e1.record()
+    barrier()
+    launches = B.launch_count()
+    clocks = sampler.stop()
+    total_ms = max_over_ranks(e0.elapsed_time(e1))
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    value = world * q * args.steps / (total_ms * 1e-3) / 1e6
+    achieved = q * B_QUERY / (kern_ms * 1e-3) / 1e9
+    checksum = float(out[:: max(1, q // 4096)].sum().item())
+
+    # ---- end to end: host buffers through the C ABI, copies inside the timed region
+    qe = q if args.e2e_queries <= 0 else min(q, args.e2e_queries)
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+        while qe > (1 << 22) and qe * 56 * world * 2 > avail:  # keep pinned buffers well inside host RAM
+            qe //= 2
+    except Exception:
+        pass
+    h_pts = torch.empty((qe, 3), dtype=torch.float64, pin_memory=True)
+    h_out = torch.empty((qe, 4), dtype=torch.float64, pin_memory=True)
+    h_pts.copy_(pts[:qe])
+    np_pts, np_out = h_pts.numpy(), h_out.numpy()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    fn.value_grad(np_pts, out=np_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        fn.value_grad(np_pts, out=np_out)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * qe * e2e_steps / e2e_s / 1e6
+    e2e_err = float(np.abs(np_out[:4096] - out[:4096].cpu().numpy()).max())
+
+    # ---- second half of the metric: 512^3 control-point solve (device resident), rank-local
+    solve = None
+    if not args.no_solve:
+        del pts, out
+        torch.cuda.empty_cache()
+        st = B.InterpolationFunctionTemplate(ORDER, SOLVE_MESH, [(0.0, 1.0)] * 3, device=local)
+        sf = torch.from_numpy(smooth_field_np(SOLVE_MESH)).to(dev)
+        sfn = st.interpolate(sf)
+        for _ in range(2):
+            st.interpolate(sf, into=sfn)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); st.interpolate(sf, into=sfn); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        sbytes = 2 * 8 * 3 * float(np.prod(SOLVE_MESH))
+        solve = {"mesh": list(SOLVE_MESH), "ms": ms, "target_ms": 50.0,
+                 "algorithmic_gbs": sbytes / ms / 1e6, "roofline_frac": sbytes / ms / 1e6 / hbm_peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        ref = CpuReference(threads)
+        ref.step(CPU_SAMPLE // 8)
+        dt = ref.step()
+        cpu = {"value": CPU_SAMPLE / dt / 1e6, "unit": "Mpts/s", "cores": threads, "kind": ref.kind,
+               "sample": ref.describe(dt)}
+
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("eval_bytes_per_query")
+                traffic = traffic * q if traffic is not None else None
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "3D cubic fp64 value+gradient eval", "value": value, "unit": "Mpts/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg3: 3D cubic 256^3 mesh, %d uniform-random queries per GPU per step, "
+                                   "value+gradient, coefficients replicated, queries sharded" % q,
+                       "mesh": list(MESH), "order": ORDER, "queries_per_gpu": q,
+                       "l2": "inputs+outputs (%.1f GB per step) exceed the 126 MB L2" % (q * B_STREAM / 1e9)},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "kernel_ms": kern_ms, "bytes_per_query": B_QUERY,
+                         "stream_only_frac": q * B_STREAM / (kern_ms * 1e-3) / 1e9 / hbm_peak},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": qe * 24, "d2h_bytes_per_step": qe * 32,
+                    "queries_per_gpu": qe, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "solve": solve,
+            "checksum": checksum,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--queries", type=int, default=Q_PER_GPU, help="queries per GPU per step")
+    ap.add_argument("--e2e-queries", type=int, default=0, help="0 = same as --queries")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()
