@@ -99,6 +99,128 @@ __device__ __forceinline__ void load_knot_window(const AxisParams<R>& a, int spa
     for (int m = 0; m < 2 * O; ++m) tk[m] = knot_at<R, O>(a, span - O + 1 + m);
 }
 
+// Reciprocal to within ~1 ulp without the IEEE division sequence: hardware seed
+// (MUFU.RCP64H / MUFU.RCP) refined by Newton steps.  Used only for basis weights
+// (tolerance 1e-12), never for span selection.
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+__device__ __forceinline__ float fast_rcp(float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    const float e = fmaf(-d, r, 1.0f);
+    return fmaf(r, e, r);
+}
+
+// One level of the Cox-de Boor triangle (BSpline.hpp:91-109) in place: on entry b
+// holds the order i-1 functions right-aligned in b[0..O]; inv[j] = 1 / (t[span+j] -
+// t[span+j-i]), j = 1..i, are the level's distinct denominators.
+template <typename R, int O>
+__device__ __forceinline__ void basis_level(const R* tk, R x, int i, const R* inv, R* b) {
+    const int ib = O - i;
+#pragma unroll
+    for (int j = 0; j <= O; ++j) {
+        if (j <= i) {
+            const int l = O - 1 - (i - j);  // local index of t[span-(i-j)]
+            const int r = O + j;            // local index of t[span+j+1]
+            R left = R(0), right = R(0);
+            if (j != 0) left = b[ib + j] * (x - tk[l]) * inv[j];
+            if (ib + j != O) right = b[ib + j + 1] * (tk[r] - x) * inv[j + 1];
+            b[ib + j] = left + right;
+        }
+    }
+}
+
+template <typename R, int O>
+__device__ __forceinline__ void level_reciprocals(const R* tk, int i, R* inv) {
+#pragma unroll
+    for (int j = 1; j <= O; ++j)
+        if (j <= i) inv[j] = fast_rcp(tk[O - 1 + j] - tk[O - 1 + j - i]);
+}
+
+// ---- fast path for uniform axes away from the clamped end knots -------------------
+// Valid when every knot the query touches (span-O+1 .. span+O, and span+1 for the
+// fix-up) is a formula knot, i.e. O + 1 <= index <= K-O-2 on non-periodic axes (always
+// on periodic ones).  The knot VALUES are the reference's, bit for bit -- (double(i)-h)
+// is exact, so stepping the index in floating point changes nothing -- which keeps the
+// span selection exact; only the divisions of the weights are replaced by a
+// Newton-refined reciprocal seeded with 1/(i dx).
+template <typename R>
+__device__ __forceinline__ R uniform_knot(const AxisParams<R>& a, R fi) {
+    using A = Arith<R>;
+    return A::add(a.lo, A::mul(A::sub(fi, a.half_extra), a.dx));
+}
+
+// Returns span; fs = R(span); x wrapped on periodic axes.  lo_i/hi_i as in locate().
+template <typename R, int O>
+__device__ __forceinline__ int locate_uniform_interior(const AxisParams<R>& a, R& x, R& fs) {
+    using A = Arith<R>;
+    if (a.periodic) {
+        const R period = A::sub(a.second, a.first);
+        const R x0 = x;
+        x = A::add(A::add(a.first, A::fmodr(A::sub(x0, a.first), period)),
+                   x0 < a.first ? period : R(0));
+    }
+    const int lo_i = O, hi_i = a.K - O - 2;
+    R g = A::floorr((x - a.lo) * a.inv_dx + a.half_extra);
+    g = fmin(fmax(g, static_cast<R>(lo_i)), static_cast<R>(hi_i));
+    int s = static_cast<int>(g);
+    fs = g;
+    while (s < hi_i && uniform_knot<R>(a, fs + R(1)) <= x) { ++s; fs += R(1); }
+    while (s > lo_i && uniform_knot<R>(a, fs) > x) { --s; fs -= R(1); }
+    return s;
+}
+
+template <typename R, int O>
+__device__ __forceinline__ void uniform_knot_window(const AxisParams<R>& a, R fs, R* tk) {
+#pragma unroll
+    for (int m = 0; m < 2 * O; ++m) tk[m] = uniform_knot<R>(a, fs + R(m - O + 1));
+}
+
+template <typename R, int O>
+__device__ __forceinline__ void level_reciprocals_uniform(const R* tk, int i, R inv_dx, R* inv) {
+    const R seed = inv_dx * (R(1) / R(i));  // i is a compile-time constant after unrolling
+#pragma unroll
+    for (int j = 1; j <= O; ++j)
+        if (j <= i) {
+            const R den = tk[O - 1 + j] - tk[O - 1 + j - i];
+            const R e = fma(-den, seed, R(1));
+            inv[j] = fma(seed, e, seed);
+        }
+}
+
+// basis_and_deriv with the uniform-seeded reciprocals.
+template <typename R, int O, bool GRAD>
+__device__ __forceinline__ void basis_uniform(const R* tk, R x, R inv_dx, R* w, R* dw) {
+#pragma unroll
+    for (int i = 0; i <= O; ++i) { w[i] = R(0); if (GRAD) dw[i] = R(0); }
+    w[O] = R(1);
+    if (O == 0) return;
+    R inv[O + 2];
+#pragma unroll
+    for (int i = 1; i < O; ++i) {
+        level_reciprocals_uniform<R, O>(tk, i, inv_dx, inv);
+        basis_level<R, O>(tk, x, i, inv, w);
+    }
+    level_reciprocals_uniform<R, O>(tk, O, inv_dx, inv);
+    if (GRAD) {
+#pragma unroll
+        for (int j = 0; j <= O; ++j) {
+            R v = R(0);
+            if (j >= 1) v = w[j] * inv[j];
+            if (j + 1 <= O) v -= w[j + 1] * inv[j + 1];
+            dw[j] = R(O) * v;
+        }
+    }
+    basis_level<R, O>(tk, x, O, inv, w);
+}
+
 // base_spline_value (BSpline.hpp:83-111): Cox-de Boor triangle of order `so`
 // (so <= O), result right-aligned in b[0..O].
 template <typename R, int O>
@@ -106,21 +228,41 @@ __device__ __forceinline__ void basis_funs(const R* tk, R x, int so, R* b) {
 #pragma unroll
     for (int i = 0; i <= O; ++i) b[i] = R(0);
     b[O] = R(1);
+    R inv[O + 2];
 #pragma unroll
     for (int i = 1; i <= O; ++i) {
         if (i <= so) {
-            const int ib = O - i;
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                const int l = O - 1 - (i - j);  // local index of t[span-(i-j)]
-                const int r = O + j;            // local index of t[span+j+1]
-                R left = R(0), right = R(0);
-                if (j != 0) left = b[ib + j] * (x - tk[l]) / (tk[r - 1] - tk[l]);
-                if (ib + j != O) right = b[ib + j + 1] * (tk[r] - x) / (tk[r] - tk[l + 1]);
-                b[ib + j] = left + right;
-            }
+            level_reciprocals<R, O>(tk, i, inv);
+            basis_level<R, O>(tk, x, i, inv, b);
         }
     }
+}
+
+// Value weights w and first-derivative weights dw of one axis from a single pass
+// over the triangle: the order O-1 functions are an intermediate of the order O
+// ones, and both use the last level's denominators
+//   dw[j] = O * ( B^{O-1}[j] / (t[span+j]-t[span+j-O]) - B^{O-1}[j+1] / (t[span+j+1]-t[span+j+1-O]) ).
+template <typename R, int O>
+__device__ __forceinline__ void basis_and_deriv(const R* tk, R x, R* w, R* dw) {
+#pragma unroll
+    for (int i = 0; i <= O; ++i) { w[i] = R(0); dw[i] = R(0); }
+    w[O] = R(1);
+    if (O == 0) return;
+    R inv[O + 2];
+#pragma unroll
+    for (int i = 1; i < O; ++i) {
+        level_reciprocals<R, O>(tk, i, inv);
+        basis_level<R, O>(tk, x, i, inv, w);
+    }
+    level_reciprocals<R, O>(tk, O, inv);
+#pragma unroll
+    for (int j = 0; j <= O; ++j) {
+        R v = R(0);
+        if (j >= 1) v = w[j] * inv[j];
+        if (j + 1 <= O) v -= w[j + 1] * inv[j + 1];
+        dw[j] = R(O) * v;
+    }
+    basis_level<R, O>(tk, x, O, inv, w);
 }
 
 // Weights of the k-th derivative along one axis: w such that
@@ -140,8 +282,8 @@ __device__ __forceinline__ void deriv_weights(const R* tk, R x, int k, R* w) {
                 if (i >= O - m) {
                     // a_i(m) = m / (t[span+i-O+m] - t[span+i-O]); local idx = global - (span-O+1)
                     R v = R(0);
-                    if (i >= O + 1 - m) v = w[i] * (R(m) / (tk[i + m - 1] - tk[i - 1]));
-                    if (i + 1 <= O) v -= w[i + 1] * (R(m) / (tk[i + m] - tk[i]));
+                    if (i >= O + 1 - m) v = w[i] * (R(m) * fast_rcp(tk[i + m - 1] - tk[i - 1]));
+                    if (i + 1 <= O) v -= w[i + 1] * (R(m) * fast_rcp(tk[i + m] - tk[i]));
                     w[i] = v;
                 }
             }

@@ -28,13 +28,7 @@ __device__ __forceinline__ long long axis_setup(const AxisParams<R>& a, R x, int
     R tk[win<O>()];
     load_knot_window<R, O>(a, span, tk);
     if (GRAD) {
-        basis_funs<R, O>(tk, x, O, w);
-        if (O >= 1) {
-            deriv_weights<R, O>(tk, x, 1, dw);
-        } else {
-#pragma unroll
-            for (int i = 0; i <= O; ++i) dw[i] = R(0);
-        }
+        basis_and_deriv<R, O>(tk, x, w, dw);
     } else {
         if (k == 0) basis_funs<R, O>(tk, x, O, w);
         else deriv_weights<R, O>(tk, x, k, w);

@@ -28,6 +28,27 @@ struct EvalArgs {
 template <typename R>
 cudaError_t launch_eval_direct(const EvalArgs<R>& a, cudaStream_t s);
 
+// Cell-binned path (3-D): tile the queries, stage each tile's coefficient brick in
+// shared memory with TMA, evaluate out of shared memory (bspl_binned.cu).
+struct BinnedScratch {
+    uint32_t* tile_of;
+    void* rec;  // sorted query records (coordinates + original index)
+    uint32_t* counts;
+    uint32_t* cursor;
+    uint32_t* work;
+    uint32_t* n_work;
+    uint32_t* next_item;
+    uint32_t* tile_total;
+    uint32_t* tile_off;
+    int max_tiles;
+};
+size_t binned_scratch_bytes(long long q, int max_tiles, size_t* offsets /*[8]*/);
+BinnedScratch binned_scratch_view(void* base, long long q, int max_tiles);
+template <typename R>
+int binned_tile_count(const EvalArgs<R>& a);  // 0 when the binned path does not apply
+template <typename R>
+cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s);
+
 // span - order per axis, int32 [q][dim]
 template <typename R>
 cudaError_t launch_locate(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s);

@@ -53,6 +53,18 @@ def solve_case(shape, order, per=None, fields=1):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which == "binned":
+        for path in ("direct", "binned"):
+            B.set_eval_path(path); print("path", path)
+            eval_case((256, 256, 256), 3, 1 << 22)
+            eval_case((256, 256, 256), 3, 1 << 24)
+            eval_case((256, 256, 256), 3, 1 << 26)
+            eval_case((256, 256, 256), 3, 1 << 28)
+            eval_case((64, 64, 64), 3, 1 << 24)
+            eval_case((512, 512, 512), 3, 1 << 26)
+            eval_case((256, 256, 256), 5, 1 << 24)
+            eval_case((256, 256, 256), 1, 1 << 24)
+        B.set_eval_path("auto")
     if which in ("all", "eval"):
         eval_case((256, 256, 256), 3, 1 << 24)
         eval_case((256, 256, 256), 3, 1 << 26)
