@@ -113,7 +113,7 @@ def run_reference(args):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -125,12 +125,14 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summarise the samples taken between the two wall-clock instants (all if None)."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.proc is None:
             return out
@@ -148,6 +150,9 @@ class ClockSampler:
             if len(r) < 9:
                 continue
             try:
+                ts = datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except ValueError:
                 continue
@@ -202,11 +207,12 @@ def run_gpu(args):
     def step():
         fn.value_grad(pts, out=out)
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    t_begin = time.time()
     B.reset_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -217,8 +223,9 @@ def run_gpu(args):
         ev[k][1].record()
     e1.record()
     barrier()
+    t_end = time.time()
     launches = B.launch_count()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, t_end)
     total_ms = max_over_ranks(e0.elapsed_time(e1))
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     value = world * q * args.steps / (total_ms * 1e-3) / 1e6

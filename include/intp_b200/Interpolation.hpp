@@ -1,0 +1,491 @@
+// intp_b200/Interpolation.hpp -- drop-in host header for the B200 implementation of the
+// BSplineInterpolation hot path.  Same namespace (`intp`), class names and member
+// signatures as the reference's user API:
+//   Mesh / MeshDimension              <- src/include/Mesh.hpp:11-116, :125-383
+//   InterpolationFunction{,1D}        <- src/include/Interpolation.hpp:17-540
+//   InterpolationFunctionTemplate{,1D}<- src/include/InterpolationTemplate.hpp:32-604
+// but every number is produced on the GPU through the C ABI of bspline_b200.h (link
+// libbspline_b200.so).  Semantics kept from the reference build used as oracle
+// (INTP_PERIODIC_NO_DUMMY_POINT): a periodic axis with N samples has period N*dx and its
+// closing sample is implicit.  Added: batched evaluate()/value_grad() on host or device
+// pointers and a batched interpolate() for many fields.
+//
+// Requires C++17.  T must equal U and be double or float.
+#ifndef INTP_B200_INTERPOLATION_HPP
+#define INTP_B200_INTERPOLATION_HPP
+
+#include <array>
+#include <cstddef>
+#include <cstdint>
+#include <iterator>
+#include <memory>
+#include <new>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../bspline_b200.h"
+
+namespace intp {
+
+// ---------------------------------------------------------------- Mesh (host container)
+template <std::size_t D>
+class MeshDimension {
+   public:
+    using size_type = std::size_t;
+    static constexpr size_type dim = D;
+    using index_type = std::array<size_type, D>;
+
+    MeshDimension() : extent_{} {}
+    MeshDimension(index_type extent) : extent_(extent) {}
+    MeshDimension(size_type n) { extent_.fill(n); }
+    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (D > 1)>>
+    MeshDimension(Args... n) : extent_{static_cast<size_type>(n)...} {}
+
+    size_type size() const {
+        return std::accumulate(extent_.begin(), extent_.end(), size_type{1}, std::multiplies<size_type>());
+    }
+    size_type dim_size(size_type d) const { return extent_[d]; }
+    size_type& dim_size(size_type d) { return extent_[d]; }
+    operator index_type() const { return extent_; }
+
+    // row-major, last index fastest
+    size_type indexing(const index_type& idx) const {
+        size_type lin = 0;
+        for (size_type d = 0; d < D; ++d) lin = lin * extent_[d] + idx[d];
+        return lin;
+    }
+    template <typename... Idx>
+    size_type indexing_safe(Idx... idx) const {
+        const index_type a{static_cast<size_type>(idx)...};
+        for (size_type d = 0; d < D; ++d)
+            if (a[d] >= extent_[d]) throw std::runtime_error("Mesh access out of range at dim " + std::to_string(d));
+        return indexing(a);
+    }
+    index_type dimwise_indices(size_type lin) const {
+        index_type idx{};
+        for (size_type d = D; d-- > 0;) { idx[d] = lin % extent_[d]; lin /= extent_[d]; }
+        return idx;
+    }
+    void resize(index_type extent) { extent_ = extent; }
+
+   private:
+    index_type extent_;
+};
+
+template <typename T, std::size_t D, typename Alloc = std::allocator<T>>
+class Mesh {
+   public:
+    using size_type = std::size_t;
+    using val_type = T;
+    static constexpr size_type dim = D;
+    using index_type = typename MeshDimension<D>::index_type;
+    using const_iterator = typename std::vector<T, Alloc>::const_iterator;
+
+    explicit Mesh(const MeshDimension<D>& md) : dims_(md), data_(md.size(), T{}) {}
+    explicit Mesh(size_type n) : Mesh(MeshDimension<D>(n)) {}
+    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (D > 1) &&
+                                                            (std::is_integral_v<Args> && ...)>>
+    explicit Mesh(Args... n) : Mesh(MeshDimension<D>(static_cast<size_type>(n)...)) {}
+    template <typename It, typename = std::enable_if_t<D == 1 && std::is_convertible_v<
+                               typename std::iterator_traits<It>::iterator_category, std::input_iterator_tag>>>
+    explicit Mesh(std::pair<It, It> range) : dims_(size_type{0}), data_(range.first, range.second) {
+        dims_ = MeshDimension<D>(data_.size());
+    }
+
+    size_type size() const { return data_.size(); }
+    size_type dim_size(size_type d) const { return dims_.dim_size(d); }
+    const MeshDimension<D>& dimension() const { return dims_; }
+    void resize(index_type extent) { dims_.resize(extent); data_.resize(dims_.size()); }
+
+    template <typename... Idx, typename = std::enable_if_t<sizeof...(Idx) == D && (std::is_integral_v<Idx> && ...)>>
+    T& operator()(Idx... i) { return data_[dims_.indexing_safe(i...)]; }
+    template <typename... Idx, typename = std::enable_if_t<sizeof...(Idx) == D && (std::is_integral_v<Idx> && ...)>>
+    const T& operator()(Idx... i) const { return data_[dims_.indexing_safe(i...)]; }
+    T& operator()(index_type i) { return data_[dims_.indexing(i)]; }
+    const T& operator()(index_type i) const { return data_[dims_.indexing(i)]; }
+
+    const T* data() const { return data_.data(); }
+    T* data() { return data_.data(); }
+    const_iterator begin() const { return data_.cbegin(); }
+    const_iterator end() const { return data_.cend(); }
+    index_type iter_indices(const_iterator it) const {
+        return dims_.dimwise_indices(static_cast<size_type>(std::distance(begin(), it)));
+    }
+
+   private:
+    MeshDimension<D> dims_;
+    std::vector<T, Alloc> data_;
+};
+
+namespace util {
+template <typename C>
+auto get_range(C& c) -> std::pair<decltype(c.begin()), decltype(c.end())> {
+    return std::make_pair(c.begin(), c.end());
+}
+}  // namespace util
+
+// ---------------------------------------------------------------- ABI plumbing
+namespace b200_detail {
+
+inline void check(int rc) {
+    if (rc == BSPL_OK) return;
+    const std::string msg = bspl_last_error();
+    switch (rc) {
+        case BSPL_ERR_DOMAIN: throw std::domain_error(msg);   // Interpolation.hpp:486
+        case BSPL_ERR_ALLOC: throw std::bad_alloc();
+        default: throw std::runtime_error(msg);               // INTP_ASSERT, util.hpp:247-258
+    }
+}
+
+template <typename T> constexpr bspl_dtype dtype_of() {
+    static_assert(std::is_same_v<T, double> || std::is_same_v<T, float>, "T must be double or float");
+    return std::is_same_v<T, double> ? BSPL_F64 : BSPL_F32;
+}
+
+struct FnDeleter { void operator()(bspl_function* p) const { bspl_function_destroy(p); } };
+struct TmDeleter { void operator()(bspl_template* p) const { bspl_template_destroy(p); } };
+using FnHandle = std::unique_ptr<bspl_function, FnDeleter>;
+using TmHandle = std::unique_ptr<bspl_template, TmDeleter>;
+
+// One axis of a template: a (min, max) pair of numbers -> uniform; a pair of iterators
+// over the abscissae -> non-uniform (the two create_knot_vector_ overloads).
+struct AxisSpec {
+    double lo = 0, hi = 0;
+    std::vector<double> coords;
+};
+template <typename X>
+AxisSpec make_axis(const std::pair<X, X>& r) {
+    AxisSpec a;
+    if constexpr (std::is_arithmetic_v<X>) {
+        a.lo = static_cast<double>(r.first);
+        a.hi = static_cast<double>(r.second);
+    } else {
+        for (auto it = r.first; it != r.second; ++it) a.coords.push_back(static_cast<double>(*it));
+        if (a.coords.size() < 2) throw std::runtime_error("an axis needs at least two coordinates");
+        a.lo = a.coords.front();
+        a.hi = a.coords.back();
+    }
+    return a;
+}
+
+inline int& default_device() {
+    static int dev = 0;
+    return dev;
+}
+
+}  // namespace b200_detail
+
+// Device used by objects constructed afterwards (CUDA ordinal; default 0).
+inline void set_device(int ordinal) { b200_detail::default_device() = ordinal; }
+
+template <typename T, std::size_t D, std::size_t O, typename U>
+class InterpolationFunctionTemplate;
+
+// ---------------------------------------------------------------- InterpolationFunction
+template <typename T, std::size_t D, std::size_t O, typename U = double>
+class InterpolationFunction {
+    static_assert(std::is_same_v<T, U>, "the B200 build evaluates real splines with T == U");
+    static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..3, order 0..5");
+
+   public:
+    using val_type = T;
+    using coord_type = U;
+    using size_type = std::size_t;
+    static constexpr size_type dim = D;
+    static constexpr size_type order = O;
+    template <typename V> using DimArray = std::array<V, D>;
+    friend class InterpolationFunctionTemplate<T, D, O, U>;
+
+    InterpolationFunction() = default;
+
+    // (periodicity, mesh, ranges...)  Interpolation.hpp:92-101
+    template <typename... Ts, typename = std::enable_if_t<sizeof...(Ts) == D>>
+    InterpolationFunction(DimArray<bool> periodicity, const Mesh<T, D>& f_mesh, std::pair<Ts, Ts>... x_ranges)
+        : InterpolationFunction(
+              InterpolationFunctionTemplate<T, D, O, U>(periodicity, f_mesh.dimension(), x_ranges...).interpolate(f_mesh)) {}
+    // all axes non-periodic  Interpolation.hpp:104-107
+    template <typename... Ts, typename = std::enable_if_t<sizeof...(Ts) == D>>
+    InterpolationFunction(const Mesh<T, D>& f_mesh, std::pair<Ts, Ts>... x_ranges)
+        : InterpolationFunction(DimArray<bool>{}, f_mesh, x_ranges...) {}
+    // 1-D iterator forms  Interpolation.hpp:49-79
+    template <typename It, typename C1, typename C2,
+              typename = std::enable_if_t<D == 1 && std::is_convertible_v<typename std::iterator_traits<It>::iterator_category,
+                                                                           std::input_iterator_tag>>>
+    InterpolationFunction(bool periodic, std::pair<It, It> f_range, std::pair<C1, C2> x_range)
+        : InterpolationFunction(DimArray<bool>{periodic}, Mesh<T, 1>(f_range),
+                                std::pair<std::common_type_t<C1, C2>, std::common_type_t<C1, C2>>(x_range)) {}
+    template <typename It, typename C1, typename C2,
+              typename = std::enable_if_t<D == 1 && std::is_convertible_v<typename std::iterator_traits<It>::iterator_category,
+                                                                           std::input_iterator_tag>>>
+    InterpolationFunction(std::pair<It, It> f_range, std::pair<C1, C2> x_range)
+        : InterpolationFunction(false, f_range, x_range) {}
+
+    // value semantics, like the reference (device storage is cloned)
+    InterpolationFunction(const InterpolationFunction& o) { *this = o; }
+    InterpolationFunction& operator=(const InterpolationFunction& o) {
+        if (this != &o) {
+            h_.reset();
+            if (o.h_) {
+                bspl_function* p = nullptr;
+                b200_detail::check(bspl_function_clone(o.h_.get(), &p));
+                h_.reset(p);
+            }
+            cache_info();
+        }
+        return *this;
+    }
+    InterpolationFunction(InterpolationFunction&&) noexcept = default;
+    InterpolationFunction& operator=(InterpolationFunction&&) noexcept = default;
+
+    // ---- single point (Interpolation.hpp:132-244); one tiny device launch per call
+    template <typename... Coords, typename = std::enable_if_t<sizeof...(Coords) == D &&
+                                                              (std::is_arithmetic_v<Coords> && ...)>>
+    val_type operator()(Coords... x) const { return (*this)(DimArray<coord_type>{static_cast<coord_type>(x)...}); }
+    val_type operator()(DimArray<coord_type> coord) const {
+        val_type v{};
+        b200_detail::check(bspl_evaluate(need(), 0, coord.data(), 1, nullptr, &v, 0, nullptr));
+        return v;
+    }
+    val_type at(DimArray<coord_type> coord) const {
+        val_type v{};
+        b200_detail::check(bspl_evaluate_at(need(), 0, coord.data(), 1, nullptr, &v, nullptr));
+        return v;
+    }
+    template <typename... Coords, typename = std::enable_if_t<sizeof...(Coords) == D &&
+                                                              (std::is_arithmetic_v<Coords> && ...)>>
+    val_type at(Coords... x) const { return at(DimArray<coord_type>{static_cast<coord_type>(x)...}); }
+
+    val_type derivative(DimArray<coord_type> coord, DimArray<size_type> derivatives) const {
+        const auto dv = to_int(derivatives);
+        val_type v{};
+        b200_detail::check(bspl_evaluate(need(), 0, coord.data(), 1, dv.data(), &v, 0, nullptr));
+        return v;
+    }
+    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (std::is_integral_v<Args> && ...)>>
+    val_type derivative(DimArray<coord_type> coord, Args... deri) const {
+        return derivative(coord, DimArray<size_type>{static_cast<size_type>(deri)...});
+    }
+    template <typename... P, typename = std::enable_if_t<sizeof...(P) == D>,
+              typename = std::void_t<decltype(std::declval<P>().first)...>>
+    val_type derivative(P... coord_order) const {
+        return derivative(DimArray<coord_type>{static_cast<coord_type>(coord_order.first)...},
+                          DimArray<size_type>{static_cast<size_type>(coord_order.second)...});
+    }
+    val_type derivative_at(DimArray<coord_type> coord, DimArray<size_type> derivatives) const {
+        const auto dv = to_int(derivatives);
+        val_type v{};
+        b200_detail::check(bspl_evaluate_at(need(), 0, coord.data(), 1, dv.data(), &v, nullptr));
+        return v;
+    }
+    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (std::is_integral_v<Args> && ...)>>
+    val_type derivative_at(DimArray<coord_type> coord, Args... deri) const {
+        return derivative_at(coord, DimArray<size_type>{static_cast<size_type>(deri)...});
+    }
+    template <typename... P, typename = std::enable_if_t<sizeof...(P) == D>,
+              typename = std::void_t<decltype(std::declval<P>().first)...>>
+    val_type derivative_at(P... coord_order) const {
+        return derivative_at(DimArray<coord_type>{static_cast<coord_type>(coord_order.first)...},
+                             DimArray<size_type>{static_cast<size_type>(coord_order.second)...});
+    }
+
+    // ---- batched entry points (new).  Host pointers: synchronous.  Device pointers: enqueued on
+    // `stream` (a cudaStream_t), no synchronisation.
+    void evaluate(const coord_type* points, size_type q, val_type* out) const {
+        b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), nullptr, out, 0, nullptr));
+    }
+    void evaluate(const std::vector<DimArray<coord_type>>& points, std::vector<val_type>& out) const {
+        out.resize(points.size());
+        evaluate(points.empty() ? nullptr : points.front().data(), points.size(), out.data());
+    }
+    void evaluate(const coord_type* points, size_type q, DimArray<size_type> derivatives, val_type* out) const {
+        const auto dv = to_int(derivatives);
+        b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), dv.data(), out, 0, nullptr));
+    }
+    // out[q][1 + D] = value, d/dx0, ..., d/dx(D-1)
+    void evaluate_value_grad(const coord_type* points, size_type q, val_type* out) const {
+        b200_detail::check(bspl_evaluate_value_grad(need(), 0, points, static_cast<int64_t>(q), out, 0, nullptr));
+    }
+    void evaluate_device(const coord_type* d_points, size_type q, val_type* d_out, void* stream = nullptr) const {
+        b200_detail::check(bspl_evaluate(need(), 0, d_points, static_cast<int64_t>(q), nullptr, d_out, 1, stream));
+    }
+    void evaluate_value_grad_device(const coord_type* d_points, size_type q, val_type* d_out,
+                                    void* stream = nullptr) const {
+        b200_detail::check(bspl_evaluate_value_grad(need(), 0, d_points, static_cast<int64_t>(q), d_out, 1, stream));
+    }
+
+    // ---- properties (Interpolation.hpp:248-267)
+    bool periodicity(size_type d) const { return periodic_[d]; }
+    bool uniform(size_type d) const { return uniform_[d]; }
+    const std::pair<coord_type, coord_type>& range(size_type d) const { return range_[d]; }
+    static constexpr size_type get_order() { return order; }
+    // plain control points of the spline (spline().control_points() without INTP_CELL_LAYOUT)
+    Mesh<T, D> control_points() const {
+        typename MeshDimension<D>::index_type ext{};
+        for (size_type d = 0; d < D; ++d) ext[d] = n_[d];
+        Mesh<T, D> m{MeshDimension<D>(ext)};
+        b200_detail::check(bspl_function_control_points(need(), 0, m.data()));
+        return m;
+    }
+    std::vector<coord_type> knots(size_type d) const {
+        std::vector<double> k(static_cast<std::size_t>(n_knots_[d]));
+        b200_detail::check(bspl_function_knots(need(), static_cast<int>(d), k.data(), static_cast<int64_t>(k.size())));
+        return std::vector<coord_type>(k.begin(), k.end());
+    }
+    const bspl_function* handle() const { return h_.get(); }
+
+   private:
+    explicit InterpolationFunction(b200_detail::FnHandle h) : h_(std::move(h)) { cache_info(); }
+    const bspl_function* need() const {
+        if (!h_) throw std::runtime_error("empty InterpolationFunction (populate it with a template's interpolate())");
+        return h_.get();
+    }
+    static std::array<int, D> to_int(const DimArray<size_type>& a) {
+        std::array<int, D> r{};
+        for (size_type d = 0; d < D; ++d) r[d] = static_cast<int>(a[d]);
+        return r;
+    }
+    void cache_info() {
+        if (!h_) return;
+        int per[BSPL_MAX_DIM], uni[BSPL_MAX_DIM];
+        int64_t n[BSPL_MAX_DIM], nk[BSPL_MAX_DIM];
+        double lo[BSPL_MAX_DIM], hi[BSPL_MAX_DIM];
+        b200_detail::check(bspl_function_info(h_.get(), nullptr, nullptr, nullptr, nullptr, n, per, uni, nk, lo, hi));
+        for (size_type d = 0; d < D; ++d) {
+            periodic_[d] = per[d] != 0;
+            uniform_[d] = uni[d] != 0;
+            n_[d] = static_cast<size_type>(n[d]);
+            n_knots_[d] = static_cast<size_type>(nk[d]);
+            range_[d] = {static_cast<coord_type>(lo[d]), static_cast<coord_type>(hi[d])};
+        }
+    }
+
+    b200_detail::FnHandle h_;
+    DimArray<bool> periodic_{};
+    DimArray<bool> uniform_{};
+    DimArray<size_type> n_{};
+    DimArray<size_type> n_knots_{};
+    DimArray<std::pair<coord_type, coord_type>> range_{};
+};
+
+// ---------------------------------------------------------------- InterpolationFunctionTemplate
+template <typename T, std::size_t D, std::size_t O, typename U = double>
+class InterpolationFunctionTemplate {
+   public:
+    using function_type = InterpolationFunction<T, D, O, U>;
+    using size_type = std::size_t;
+    using coord_type = U;
+    using val_type = T;
+    static constexpr size_type dim = D;
+    static constexpr size_type order = O;
+    template <typename V> using DimArray = std::array<V, D>;
+    using MeshDim = MeshDimension<D>;
+
+    // (periodicity, mesh dimension, ranges...)  InterpolationTemplate.hpp:60-79
+    template <typename... Ts, typename = std::enable_if_t<sizeof...(Ts) == D>>
+    InterpolationFunctionTemplate(DimArray<bool> periodicity, MeshDim mesh_dimension, std::pair<Ts, Ts>... x_ranges)
+        : mesh_dimension_(mesh_dimension) {
+        const std::array<b200_detail::AxisSpec, D> ax{b200_detail::make_axis(x_ranges)...};
+        int64_t n[D];
+        int per[D];
+        double lo[D], hi[D];
+        const double* coords[D];
+        for (size_type d = 0; d < D; ++d) {
+            n[d] = static_cast<int64_t>(mesh_dimension.dim_size(d));
+            per[d] = periodicity[d] ? 1 : 0;
+            lo[d] = ax[d].lo;
+            hi[d] = ax[d].hi;
+            coords[d] = ax[d].coords.empty() ? nullptr : ax[d].coords.data();
+            if (coords[d] && ax[d].coords.size() != mesh_dimension.dim_size(d) + (periodicity[d] ? 1 : 0))
+                throw std::runtime_error("Inconsistency between knot number and interpolated value number at dimension " +
+                                         std::to_string(d));
+        }
+        bspl_template* t = nullptr;
+        b200_detail::check(bspl_template_create(b200_detail::dtype_of<T>(), static_cast<int>(D), static_cast<int>(O), n, per,
+                                                lo, hi, coords, b200_detail::default_device(), &t));
+        h_.reset(t);
+    }
+    // 1-D forms  InterpolationTemplate.hpp:88-102
+    template <typename C1, typename C2, size_type DD = D, typename = std::enable_if_t<DD == 1>>
+    InterpolationFunctionTemplate(bool periodicity, size_type f_length, std::pair<C1, C2> x_range)
+        : InterpolationFunctionTemplate(DimArray<bool>{periodicity}, MeshDim{f_length},
+                                        std::pair<std::common_type_t<C1, C2>, std::common_type_t<C1, C2>>(x_range)) {}
+    template <typename C1, typename C2, size_type DD = D, typename = std::enable_if_t<DD == 1>>
+    InterpolationFunctionTemplate(size_type f_length, std::pair<C1, C2> x_range)
+        : InterpolationFunctionTemplate(false, f_length, x_range) {}
+    // all axes non-periodic  InterpolationTemplate.hpp:111-116
+    template <typename... Ts, typename = std::enable_if_t<sizeof...(Ts) == D>>
+    InterpolationFunctionTemplate(MeshDim mesh_dimension, std::pair<Ts, Ts>... x_ranges)
+        : InterpolationFunctionTemplate(DimArray<bool>{}, mesh_dimension, x_ranges...) {}
+
+    // interpolate(mesh)  InterpolationTemplate.hpp:118-133
+    function_type interpolate(const Mesh<T, D>& f_mesh) const {
+        check_mesh(f_mesh);
+        bspl_function* f = nullptr;
+        b200_detail::check(bspl_template_interpolate(h_.get(), f_mesh.data(), 1, 0, nullptr, &f));
+        return function_type(b200_detail::FnHandle(f));
+    }
+    template <typename It, size_type DD = D, typename = std::enable_if_t<DD == 1>>
+    function_type interpolate(std::pair<It, It> f_range) const {
+        return interpolate(Mesh<T, 1>(f_range));
+    }
+    // interpolate(function&, mesh)  InterpolationTemplate.hpp:136-143
+    void interpolate(function_type& interp, const Mesh<T, D>& f_mesh) const {
+        check_mesh(f_mesh);
+        if (!interp.h_) { interp = interpolate(f_mesh); return; }
+        b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), f_mesh.data(), 1, 0, nullptr));
+        interp.cache_info();
+    }
+    // device-resident mesh (row-major, same shape), enqueued on `stream`
+    function_type interpolate_device(const T* d_mesh, void* stream = nullptr) const {
+        bspl_function* f = nullptr;
+        b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
+        return function_type(b200_detail::FnHandle(f));
+    }
+    const MeshDim& mesh_dimension() const { return mesh_dimension_; }
+    const bspl_template* handle() const { return h_.get(); }
+
+   private:
+    void check_mesh(const Mesh<T, D>& m) const {
+        for (size_type d = 0; d < D; ++d)
+            if (m.dim_size(d) != mesh_dimension_.dim_size(d)) throw std::runtime_error("mesh shape differs from the template's");
+    }
+    MeshDim mesh_dimension_;
+    b200_detail::TmHandle h_;
+};
+
+// ---------------------------------------------------------------- 1-D conveniences
+template <std::size_t O = 3, typename T = double, typename U = double>
+class InterpolationFunction1D : public InterpolationFunction<T, 1, O, U> {
+    using base = InterpolationFunction<T, 1, O, U>;
+
+   public:
+    // default x range [0, N-1], or [0, N] when periodic  Interpolation.hpp:518-533
+    template <typename It>
+    InterpolationFunction1D(std::pair<It, It> f_range, bool periodicity = false)
+        : InterpolationFunction1D(
+              std::make_pair(U{}, static_cast<U>(std::distance(f_range.first, f_range.second) - (periodicity ? 0 : 1))),
+              f_range, periodicity) {}
+    template <typename C1, typename C2, typename It>
+    InterpolationFunction1D(std::pair<C1, C2> x_range, std::pair<It, It> f_range, bool periodicity = false)
+        : base(periodicity, f_range, x_range) {}
+};
+
+template <std::size_t O, typename T = double, typename U = double>
+class InterpolationFunctionTemplate1D : public InterpolationFunctionTemplate<T, 1, O, U> {
+    using base = InterpolationFunctionTemplate<T, 1, O, U>;
+
+   public:
+    InterpolationFunctionTemplate1D(typename base::size_type f_length, bool periodicity = false)
+        : InterpolationFunctionTemplate1D(std::make_pair(U{}, static_cast<U>(f_length - 1)), f_length, periodicity) {}
+    template <typename C1, typename C2>
+    InterpolationFunctionTemplate1D(std::pair<C1, C2> x_range, typename base::size_type f_length, bool periodicity = false)
+        : base(periodicity, f_length, x_range) {}
+};
+
+}  // namespace intp
+
+#endif  // INTP_B200_INTERPOLATION_HPP

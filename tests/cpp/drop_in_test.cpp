@@ -1,0 +1,145 @@
+// Drop-in check of include/intp_b200/Interpolation.hpp: the scenarios of the reference's
+// test/src/interpolation-test.cpp, written against the same class names, with the
+// Mathematica golden vectors supplied through golden_vectors.inc (generated from
+// tests/golden/reference_vectors.json by tests/test_cpp_dropin.py).  Needs a GPU.
+#include <intp_b200/Interpolation.hpp>
+
+#include <cmath>
+#include <cstdio>
+#include <vector>
+
+#include "golden_vectors.inc"  // namespace golden { const std::vector<double> f, coords_1d, ...; }
+
+using namespace intp;
+
+static int failures = 0;
+static void expect(bool ok, const char* what, double err = 0) {
+    std::printf("%-58s %s  (%.3g)\n", what, ok ? "ok" : "FAILED", err);
+    if (!ok) ++failures;
+}
+template <typename F>
+static double rel_err(F&& f, const std::vector<double>& pts, std::size_t dim, const std::vector<double>& vals) {
+    double e = 0, l2 = 0;
+    for (std::size_t i = 0; i < vals.size(); ++i) {
+        const double v = f(&pts[i * dim]);
+        e += (v - vals[i]) * (v - vals[i]);
+        l2 += vals[i] * vals[i];
+    }
+    return std::sqrt(e / l2);
+}
+
+int main() {
+    constexpr double tol = 1e-14;
+    using namespace golden;
+
+    // 1-D, orders 3 / 1 / 0, extrapolation
+    InterpolationFunction1D<3> interp1{std::make_pair(0, .5 * (f.size() - 1)), util::get_range(f)};
+    double d = rel_err([&](const double* x) { return interp1(x[0]); }, coords_1d_half, 1, vals_1d);
+    expect(d < tol, "1D cubic", d);
+    expect(std::abs(interp1(-.5) - extrapolate_left[1]) < tol, "1D extrapolation left");
+    expect(std::abs(interp1(6.5) - extrapolate_right[1]) < tol, "1D extrapolation right");
+    d = rel_err([&](const double* x) { return interp1.derivative_at(std::make_pair(x[0], 1)); }, coords_1d_half, 1,
+                vals_1d_derivative_1);
+    expect(d < tol, "1D derivative", d);
+    InterpolationFunction1D<1> lin(util::get_range(f));
+    d = rel_err([&](const double* x) { return lin(x[0]); }, coords_1d, 1, [&] {
+        std::vector<double> v;
+        for (double c : coords_1d) { auto i = static_cast<std::size_t>(std::floor(c)); v.push_back(f[i] + (f[i + 1] - f[i]) * (c - double(i))); }
+        return v; }());
+    expect(d < tol, "1D linear", d);
+
+    // 1-D periodic quartic (INTP_PERIODIC_NO_DUMMY_POINT semantics)
+    std::vector<double> fp(f.begin(), f.end() - 1);
+    InterpolationFunction1D<4> interp1p(util::get_range(fp), true);
+    d = rel_err([&](const double* x) { return interp1p(x[0]); }, coords_1d, 1, vals_1d_periodic);
+    expect(d < tol, "1D periodic quartic", d);
+    expect(std::abs(interp1p(coords_1d[0] - 12.) - vals_1d_periodic[0]) < tol, "periodic wrap left");
+    expect(std::abs(interp1p(coords_1d[0] + 12.) - vals_1d_periodic[0]) < tol, "periodic wrap right");
+    d = rel_err([&](const double* x) { return interp1p.derivative_at(std::make_pair(x[0], 1)); }, coords_1d, 1,
+                vals_1d_derivative_periodic);
+    expect(d < tol, "1D periodic derivative", d);
+
+    // 2-D 5x5 cubic, bounds check, periodic y
+    Mesh<double, 2> f2d{5, 5};
+    for (std::size_t i = 0; i < 5; ++i) for (std::size_t j = 0; j < 5; ++j) f2d(i, j) = f2[i * 5 + j];
+    InterpolationFunction<double, 2, 3> interp2{f2d, std::make_pair(0., 4.), std::make_pair(0., 4.)};
+    expect(interp2.uniform(0) && interp2.uniform(1), "uniform flags");
+    d = rel_err([&](const double* x) { return interp2(x[0], x[1]); }, coords_2d, 2, vals_2d);
+    expect(d < tol, "2D cubic", d);
+    d = rel_err([&](const double* x) { return interp2.derivative_at(std::array<double, 2>{x[0], x[1]}, 2, 1); }, coords_2d,
+                2, vals_2d_derivative_x2_y1);
+    expect(d < tol, "2D derivative (2,1)", d);
+    bool threw = false;
+    try { interp2.at(-1, 1); } catch (const std::domain_error&) { threw = true; }
+    expect(threw, "at() throws std::domain_error out of range");
+    Mesh<double, 2> f2py{5, 4};
+    for (std::size_t i = 0; i < 5; ++i) for (std::size_t j = 0; j < 4; ++j) f2py(i, j) = f2[i * 5 + j];
+    InterpolationFunction<double, 2, 3> interp2p({false, true}, f2py, std::make_pair(0., 4.), std::make_pair(0., 4.));
+    d = rel_err([&](const double* x) { return interp2p(x[0], x[1]); }, coords_2d, 2, vals_2d_periodic);
+    expect(d < tol, "2D periodic y", d);
+
+    // 3-D 5x6x7 cubic + derivative (1,0,3), template reuse, batched entry points
+    Mesh<double, 3> f3d{5, 6, 7};
+    for (std::size_t i = 0; i < 210; ++i) f3d(f3d.dimension().dimwise_indices(i)) = f3[i];
+    InterpolationFunctionTemplate<double, 3, 3> tmpl(f3d.dimension(), std::make_pair(0., 4.), std::make_pair(0., 5.),
+                                                     std::make_pair(0., 6.));
+    auto interp3 = tmpl.interpolate(f3d);
+    d = rel_err([&](const double* x) { return interp3(x[0], x[1], x[2]); }, coords_3d, 3, vals_3d);
+    expect(d < tol, "3D cubic through a template", d);
+    d = rel_err([&](const double* x) { return interp3.derivative_at(std::array<double, 3>{x[0], x[1], x[2]}, {1, 0, 3}); },
+                coords_3d, 3, vals_3d_derivative_x1_y0_z3);
+    expect(d < tol, "3D derivative (1,0,3)", d);
+    std::vector<double> batch(vals_3d.size());
+    interp3.evaluate(coords_3d.data(), batch.size(), batch.data());
+    double e = 0, l2 = 0;
+    for (std::size_t i = 0; i < batch.size(); ++i) { e += (batch[i] - vals_3d[i]) * (batch[i] - vals_3d[i]); l2 += vals_3d[i] * vals_3d[i]; }
+    expect(std::sqrt(e / l2) < tol, "batched evaluate(points, out)", std::sqrt(e / l2));
+    std::vector<double> vg(4 * vals_3d.size());
+    interp3.evaluate_value_grad(coords_3d.data(), vals_3d.size(), vg.data());
+    double worst = 0;
+    for (std::size_t i = 0; i < vals_3d.size(); ++i) {
+        std::array<double, 3> c{coords_3d[3 * i], coords_3d[3 * i + 1], coords_3d[3 * i + 2]};
+        worst = std::max(worst, std::abs(vg[4 * i] - interp3(c)));
+        worst = std::max(worst, std::abs(vg[4 * i + 1] - interp3.derivative(c, 1, 0, 0)));
+        worst = std::max(worst, std::abs(vg[4 * i + 2] - interp3.derivative(c, 0, 1, 0)));
+        worst = std::max(worst, std::abs(vg[4 * i + 3] - interp3.derivative(c, 0, 0, 1)));
+    }
+    expect(worst < 1e-13, "fused value+gradient == separate calls", worst);
+    auto copy = interp3;  // value semantics
+    expect(copy(coords_3d[0], coords_3d[1], coords_3d[2]) == interp3(coords_3d[0], coords_3d[1], coords_3d[2]), "copy");
+    InterpolationFunction<double, 3, 3> into;
+    tmpl.interpolate(into, f3d);
+    expect(into(1., 2., 3.) == interp3(1., 2., 3.), "interpolate(function&, mesh)");
+    expect(!interp3.periodicity(0) && !interp3.periodicity(1) && !interp3.periodicity(2), "periodicity()");
+    expect(interp3.range(1).first == 0. && interp3.range(1).second == 5., "range()");
+
+    // non-uniform axes
+    InterpolationFunction1D<3> nu(util::get_range(input_coords_1d), util::get_range(f));
+    d = rel_err([&](const double* x) { return nu(x[0]); }, coords_1d, 1, vals_1d_nonuniform);
+    expect(d < tol && !nu.uniform(0), "1D non-uniform cubic", d);
+    InterpolationFunction1D<4> nup(util::get_range(input_coords_1d), util::get_range(fp), true);
+    d = rel_err([&](const double* x) { return nup(x[0]); }, coords_1d, 1, vals_1d_nonuniform_periodic);
+    expect(d < tol, "1D non-uniform periodic quartic", d);
+    Mesh<double, 2> f2px{4, 5};
+    for (std::size_t i = 0; i < 4; ++i) for (std::size_t j = 0; j < 5; ++j) f2px(i, j) = f2[i * 5 + j];
+    InterpolationFunction<double, 2, 3> mixed({true, false}, f2px, std::make_pair(0., 4.),
+                                              util::get_range(nonuniform_coord_for_2d));
+    d = rel_err([&](const double* x) { return mixed(x[0], x[1]); }, coords_2d, 2, vals_2d_X_periodic_Y_nonuniform);
+    expect(d < tol, "2D x-periodic, y non-uniform", d);
+
+    // float build (T = U = float): circle, interpolation-test.cpp:674-703 reduced to one component
+    {
+        constexpr std::size_t n = 31;
+        std::vector<float> cx;
+        for (std::size_t i = 0; i < n; ++i) cx.push_back(std::cos(2.f * 3.14159265358979f * float(i) / n));
+        InterpolationFunction1D<3, float, float> circ(std::make_pair(0.f, 2.f * 3.14159265358979f), util::get_range(cx), true);
+        float err = 0;
+        for (std::size_t i = 0; i < 1024; ++i) {
+            const float th = 2.f * 3.14159265358979f * float(i) / 1024;
+            err = std::max(err, std::abs(circ(th) - std::cos(th)));
+        }
+        expect(err < 2e-4f, "float periodic cubic on cos", err);
+    }
+    std::printf("%d failure(s)\n", failures);
+    return failures;
+}

@@ -1,0 +1,41 @@
+"""The C++ drop-in header (include/intp_b200/Interpolation.hpp): compiles with the host
+compiler alone (CPU check) and reproduces the reference's interpolation-test scenarios on
+the GPU (gpu check)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def _build(tmp_path, lib_built):
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["interpolation"]
+    inc = tmp_path / "golden_vectors.inc"
+    with open(inc, "w") as fh:
+        fh.write("#include <vector>\nnamespace golden {\n")
+        for k, v in g.items():
+            fh.write("const std::vector<double> %s = {%s};\n" % (k, ", ".join(repr(float(x)) for x in v)))
+        fh.write("}\n")
+    exe = tmp_path / "drop_in_test"
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", str(tmp_path),
+           os.path.join(ROOT, "tests", "cpp", "drop_in_test.cpp"), "-o", str(exe),
+           "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg]
+    subprocess.check_call(cmd)
+    return exe
+
+
+def test_header_compiles_and_links(tmp_path, lib_built):
+    assert os.path.exists(_build(tmp_path, lib_built))
+
+
+@pytest.mark.gpu
+def test_reference_scenarios_through_cpp_header(tmp_path, lib_built):
+    exe = _build(tmp_path, lib_built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
