@@ -66,6 +66,7 @@ struct AxisLU {
     const R* right;   // [n][p]  side(i, n-p+c) at [i*p + c]          (cyclic)
     int bottom_len;   // entries j >= bottom_len are exactly zero
     int right_len;    // entries i >= right_len are exactly zero (rows above the main band only)
+    int bottom_sig;   // entries j >= bottom_sig are below 1e-30 of the largest (chunked sweeps only)
 };
 
 // Geometry of one sweep over a (field, axis0, axis1, axis2) array: lines run
@@ -77,8 +78,18 @@ struct SweepGeom {
     long long ms[3];         // their element strides
 };
 
+// chunk == 0: exact sequential sweep, one thread per line (bit-identical to the reference).
+// chunk  > 0: chunk-parallel sweep (few long lines); scratch holds y (scratch_y_elems) followed
+// by lines*max(P,1) tail values.
+struct SweepPlan {
+    int chunk;
+    int window;
+    void* scratch;
+    long long scratch_y_elems;
+};
+SweepPlan plan_sweep(int n, long long lines, int window, int cyclic, int bottom_sig);
 template <typename R>
-cudaError_t launch_sweep(const AxisLU<R>& lu, const SweepGeom& g, R* data, cudaStream_t s);
+cudaError_t launch_sweep(const AxisLU<R>& lu, const SweepGeom& g, R* data, const SweepPlan& plan, cudaStream_t s);
 
 // f (compact, [fields][n0][n1][n2]) -> padded coefficient array, rotating each
 // periodic axis by +shift[d] (InterpolationTemplate.hpp:451-462).

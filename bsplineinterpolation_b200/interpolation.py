@@ -283,6 +283,26 @@ class InterpolationFunctionTemplate:
         return InterpolationFunction(_handle=out)
 
 
+    def sweep_axis(self, axis, data, outer_sizes, outer_strides, line_stride, stream=None):
+        """In-place banded/cyclic solve of template axis `axis` along every line of a device
+        tensor (one stage of the separable solve); see bspl_template_sweep_axis."""
+        import torch
+        assert _is_device(data)
+        _a, m = _i64(list(outer_sizes))
+        _b, ms = _i64(list(outer_strides))
+        sp = stream if stream is not None else torch.cuda.current_stream(data.device).cuda_stream
+        check(lib().bspl_template_sweep_axis(self._h, int(axis), C.c_void_p(data.data_ptr()), m, ms,
+                                             int(line_stride), C.c_void_p(sp)))
+        return data
+
+    def function_from_control_points(self, ctrl):
+        """Wrap solved plain control points (numpy or CUDA tensor, leading field axis optional)."""
+        keep, ptr, n_fields, dev, sp = self._mesh_ptr(ctrl)
+        out = C.c_void_p()
+        check(lib().bspl_template_function_from_ctrl(self._h, ptr, n_fields, dev, sp, C.byref(out)))
+        return InterpolationFunction(_handle=out)
+
+
 class BSpline:
     @staticmethod
     def from_knots(order, periodicity, knots, control_points, dtype=np.float64, device=0):

@@ -78,6 +78,21 @@ int bspl_template_interpolate(const bspl_template* t, const void* f, int64_t n_f
 int bspl_template_interpolate_into(const bspl_template* t, bspl_function* fn, const void* f,
                                    int64_t n_fields, int on_device, void* stream);
 
+/* One stage of solve_for_control_points_ on caller-owned DEVICE memory: the banded /
+ * cyclic solve of template axis `axis` (solvers_[axis], InterpolationTemplate.hpp:515)
+ * applied in place to every line of a strided array.  A line has n[axis] elements
+ * `line_stride` apart; lines are enumerated by up to three outer indices i0 < m[0],
+ * i1 < m[1], i2 < m[2] at element offsets i0*ms[0] + i1*ms[1] + i2*ms[2] (m[2] should be
+ * the contiguous-most).  The periodic-axis rotation of the right-hand side
+ * (:451-462) is NOT applied here.  Building block of the slab-sharded multi-GPU solve
+ * (sweep local axes, all-to-all, sweep the remaining axis). */
+int bspl_template_sweep_axis(const bspl_template* t, int axis, void* data, const int64_t* m,
+                             const int64_t* ms, int64_t line_stride, void* stream);
+/* Wrap already-solved plain control points ([n_fields][n0]...[nD-1], host or device) into
+ * a function of this template (load_ctrlPts, BSpline.hpp:229-242). */
+int bspl_template_function_from_ctrl(const bspl_template* t, const void* ctrl, int64_t n_fields,
+                                     int on_device, void* stream, bspl_function** out);
+
 /* BSpline(periodicity, ctrl_pts, knot_iter_pairs...) (BSpline.hpp:188-210): a
  * spline straight from knot vectors and control points (host pointers).
  * n_knots[d] - n_ctrl[d] must be order+1, or 2*order+1 on periodic axes. */

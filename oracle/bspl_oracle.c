@@ -443,6 +443,8 @@ bsplo_spline* bsplo_create(int dim, int order, const int64_t* n, const int* peri
                            const double* lo, const double* hi, const double* const* coords,
                            int with_solver) {
     if (dim < 1 || dim > BSPLO_MAXD || order < 0 || order > BSPLO_MAXO) return NULL;
+    for (int d = 0; d < dim; ++d)
+        if (n[d] < order + 1 || n[d] < 2) return NULL; /* the reference has no such guard */
     bsplo_spline* s = (bsplo_spline*)calloc(1, sizeof *s);
     s->dim = dim;
     s->order = order;

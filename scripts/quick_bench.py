@@ -72,6 +72,12 @@ if __name__ == "__main__":
         eval_case((64, 64, 64), 3, 1 << 24)
         eval_case((1024, 1024), 3, 1 << 24)
         eval_case((1 << 24,), 5, 1 << 24, per=[True])
+    if which == "long":
+        solve_case((1 << 24,), 5, per=[True])
+        solve_case((1 << 24,), 3)
+        solve_case((1 << 20,), 3, per=[True])
+        solve_case((1024, 1024), 3, per=[True, True])
+        solve_case((4096, 4096), 3, per=[True, False])
     if which in ("all", "solve"):
         solve_case((256, 256, 256), 3)
         solve_case((512, 512, 512), 3)

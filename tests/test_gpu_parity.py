@@ -281,3 +281,31 @@ def test_binned_tma_path_matches_direct_and_oracle(pkg, order, periodic):
     inside = np.all((pts >= rlo) & (pts <= rhi), axis=1) | np.array(periodic).all()
     _close(v_b[inside], o.eval(pts[inside]))
     _close(g_b[inside, 2], o.deriv(pts[inside], [0, 1, 0]))
+
+
+@pytest.mark.parametrize("order,periodic", [(1, True), (2, False), (3, False), (3, True), (4, True), (5, False), (5, True)])
+def test_chunk_parallel_solve_long_lines(pkg, order, periodic):
+    """Few, long lines take the chunk-parallel sweep (warm-up window instead of the sequential
+    dependency).  Control points must match the sequential reference algorithm to 1e-13 of
+    the field scale (they are normally bit-identical: the truncation error is < 1e-23)."""
+    rng = np.random.default_rng(900 + order)
+    n = 200_003
+    f = np.cos(np.arange(n) * 0.001) + 0.3 * rng.standard_normal(n)
+    o = OracleSpline(order, (n,), [periodic], lo=[-1.0], hi=[3.0], f=f)
+    fn = pkg.InterpolationFunction(order, f, [(-1.0, 3.0)], [periodic])
+    c, ref = fn.control_points(), o.control_points()
+    assert np.abs(c - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert (c != ref).mean() < 1e-3  # bit-identical except, at most, isolated last-bit ties
+    pts = rng.uniform(-1.0, 3.0, 5000)
+    _close(fn(pts), o.eval(pts))
+    # 2-D: 3 long lines per axis-0 sweep are not enough to chunk, the long axis is
+    shape = (8, 50_000)
+    f2 = rng.standard_normal(shape)
+    o2 = OracleSpline(order, shape, [False, periodic], lo=[0, 0], hi=[1, 1], f=f2)
+    fn2 = pkg.InterpolationFunction(order, f2, [(0.0, 1.0), (0.0, 1.0)], [False, periodic])
+    assert np.abs(fn2.control_points() - o2.control_points()).max() <= 1e-13 * np.abs(o2.control_points()).max()
+    shape = (40_000, 8)
+    f3 = rng.standard_normal(shape)
+    o3 = OracleSpline(order, shape, [periodic, False], lo=[0, 0], hi=[1, 1], f=f3)
+    fn3 = pkg.InterpolationFunction(order, f3, [(0.0, 1.0), (0.0, 1.0)], [periodic, False])
+    assert np.abs(fn3.control_points() - o3.control_points()).max() <= 1e-13 * np.abs(o3.control_points()).max()
