@@ -118,6 +118,19 @@ cudaError_t launch_fill_ghosts(const GhostGeom& g, R* data, cudaStream_t s);
 template <typename R>
 cudaError_t launch_unpad_copy(const CopyGeom& g, const R* src_padded, R* dst_compact, cudaStream_t s);
 
+// Batched transpose of the last two axes through shared memory:
+//   dst[(b0, b1), rot_q(q), rot_p(p)] = src[(b0, b1), p, q]     (src q-contiguous, dst p-contiguous)
+// with optional rotation of every index by +shift (mod extent) on the destination side.
+// (b0, b1) are two outer batch indices with independent strides (fields, leading axis).
+struct TransposeGeom {
+    int nb0, nb1, np, nq;
+    long long src_b0, src_b1, src_p;            // src element (b0,b1,p,q) at b0*src_b0 + b1*src_b1 + p*src_p + q
+    long long dst_b0, dst_b1, dst_q;            // dst element at b0*dst_b0 + b1'*dst_b1 + q'*dst_q + p'
+    int shift_b1, shift_p, shift_q;
+};
+template <typename R>
+cudaError_t launch_transpose(const TransposeGeom& g, const R* src, R* dst, cudaStream_t s);
+
 void count_launch(int n = 1);
 
 }  // namespace bspl

@@ -72,6 +72,17 @@ if __name__ == "__main__":
         eval_case((64, 64, 64), 3, 1 << 24)
         eval_case((1024, 1024), 3, 1 << 24)
         eval_case((1 << 24,), 5, 1 << 24, per=[True])
+    if which == "fields":
+        F, shape, Q = 4096, (128, 128), 1 << 20
+        t = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 2)
+        f = torch.rand((F,) + shape, dtype=torch.float64, device="cuda")
+        fn = t.interpolate(f)
+        print("solve 4096 fields: %.3f ms" % timeit(lambda: t.interpolate(f, into=fn))[1])
+        pts = torch.rand((Q, 2), dtype=torch.float64, device="cuda")
+        out = torch.empty((F, Q), dtype=torch.float64, device="cuda")
+        ms = timeit(lambda: fn.evaluate_fields(pts, out=out), reps=3, warm=1)[1]
+        print("evaluate_fields 4096 x 2^20: %.2f ms -> %.2f G(query,field)/s, %.0f GB/s algorithmic (152 B each)" % (
+            ms, F * Q / ms / 1e6, F * Q * 152 / ms / 1e6))
     if which == "long":
         solve_case((1 << 24,), 5, per=[True])
         solve_case((1 << 24,), 3)

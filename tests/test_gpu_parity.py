@@ -309,3 +309,55 @@ def test_chunk_parallel_solve_long_lines(pkg, order, periodic):
     o3 = OracleSpline(order, shape, [periodic, False], lo=[0, 0], hi=[1, 1], f=f3)
     fn3 = pkg.InterpolationFunction(order, f3, [(0.0, 1.0), (0.0, 1.0)], [periodic, False])
     assert np.abs(fn3.control_points() - o3.control_points()).max() <= 1e-13 * np.abs(o3.control_points()).max()
+
+
+@pytest.mark.parametrize("dim,order,periodic", [(1, 3, (True,)), (2, 3, (False, True)), (3, 3, (False, False, False)),
+                                                 (3, 2, (True, False, True)), (2, 5, (False, False))])
+def test_fp32_within_1e5_of_fp64_reference(pkg, dim, order, periodic):
+    """T = U = float build: values, gradient and control points within 1e-5 relative of the fp64
+    oracle (north star: 1e-5 for fp32); knots are built in float arithmetic like the reference's
+    coord_type = float instantiation."""
+    rng = np.random.default_rng(70 + dim + order)
+    shape = small_shapes(dim, order, periodic)
+    lo = np.zeros(dim); hi = np.arange(1, dim + 1, dtype=np.float64)
+    f = smooth_field(shape, rng).astype(np.float32)
+    o = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=f.astype(np.float64))
+    fn = pkg.InterpolationFunction(order, f, _ranges(lo, hi), periodic, dtype=np.float32)
+    assert fn.dtype == np.float32
+    ref_c = o.control_points()
+    assert np.abs(fn.control_points() - ref_c).max() <= 1e-5 * np.abs(ref_c).max()
+    # stay half a cell away from the ends: float knots differ from double knots by an ulp(float)
+    pts = (lo + (0.02 + 0.96 * rng.uniform(0, 1, (4000, dim))) * (hi - lo)).astype(np.float32)
+    ref = o.eval(pts.astype(np.float64))
+    got = fn(pts)
+    assert got.dtype == np.float32
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+    vg = fn.value_grad(pts)
+    for d in range(dim):
+        dv = [0] * dim; dv[d] = 1
+        g = o.deriv(pts.astype(np.float64), dv)
+        assert np.abs(vg[:, 1 + d] - g).max() <= 2e-4 * np.abs(g).max()  # derivative: one order less smooth
+    if dim == 3:
+        import torch
+        try:
+            pkg.set_eval_path("binned")
+            b = fn.value_grad(torch.from_numpy(pts).cuda()).cpu().numpy()
+        finally:
+            pkg.set_eval_path("auto")
+        assert np.abs(b - vg).max() <= 1e-5 * np.abs(vg).max()
+
+
+def test_many_fields_cfg5_shape(pkg):
+    """cfg5 scaled down: fields on one 128x128 cubic mesh, one query set for all fields."""
+    import torch
+    rng = np.random.default_rng(8)
+    F, shape, Q = 24, (128, 128), 5000
+    fields = rng.standard_normal((F,) + shape)
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0), (0.0, 1.0)])
+    fn = t.interpolate(torch.from_numpy(fields).cuda())
+    pts = rng.uniform(0, 1, (Q, 2))
+    allv = fn.evaluate_fields(torch.from_numpy(pts).cuda()).cpu().numpy()
+    for k in (0, 7, F - 1):
+        o = OracleSpline(3, shape, [0, 0], lo=[0, 0], hi=[1, 1], f=fields[k])
+        assert np.array_equal(fn.control_points(k), o.control_points())
+        _close(allv[k], o.eval(pts))
