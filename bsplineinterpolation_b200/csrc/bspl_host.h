@@ -10,6 +10,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <new>
 #include <stdexcept>
 #include <vector>
 
@@ -132,6 +134,27 @@ struct HostAxis {
     }
 };
 
+// Zero-initialised array whose untouched pages cost nothing (calloc): the corner strips of a
+// long cyclic axis are almost entirely zero.
+template <typename R>
+struct ZeroBuf {
+    R* p = nullptr;
+    size_t count = 0;
+    ZeroBuf() = default;
+    ZeroBuf(const ZeroBuf&) = delete;
+    ZeroBuf& operator=(const ZeroBuf&) = delete;
+    ~ZeroBuf() { std::free(p); }
+    void assign(size_t n) {
+        std::free(p);
+        p = static_cast<R*>(std::calloc(n ? n : 1, sizeof(R)));
+        if (!p) throw std::bad_alloc();
+        count = n;
+    }
+    R& operator[](size_t i) { return p[i]; }
+    const R& operator[](size_t i) const { return p[i]; }
+    size_t size() const { return count; }
+};
+
 // LU factors of a banded (optionally cyclic) n x n matrix, no pivoting.
 // Storage: main band by rows, the cyclic corners as two thin dense strips.
 template <typename R>
@@ -140,15 +163,18 @@ struct BandFactor {
     int p = 0, q = 0;
     bool cyclic = false;
     std::vector<R> band;    // [n][p+q+1]: A(i, j) at band[i*(p+q+1) + j-i+p]
-    std::vector<R> right;   // [n][p]:     A(i, n-p+c)  (rows above the band)
-    std::vector<R> bottom;  // [q][n]:     A(n-q+r, j)  (columns left of the band)
+    ZeroBuf<R> right;       // [n][p]:     A(i, n-p+c)  (rows above the band)
+    ZeroBuf<R> bottom;      // [q][n]:     A(n-q+r, j)  (columns left of the band)
+    int64_t right_rows = 0;   // rows >= right_rows of the right strip were never written
+    int64_t bottom_cols = 0;  // columns >= bottom_cols of the bottom strip were never written
 
     void init(int64_t n_, int p_, int q_, bool cyclic_) {
         n = n_; p = p_; q = q_; cyclic = cyclic_;
         band.assign(static_cast<size_t>(n) * (p + q + 1), R(0));
         if (cyclic) {
-            right.assign(static_cast<size_t>(n) * std::max(p, 1), R(0));
-            bottom.assign(static_cast<size_t>(n) * std::max(q, 1), R(0));
+            right.assign(static_cast<size_t>(n) * std::max(p, 1));
+            bottom.assign(static_cast<size_t>(n) * std::max(q, 1));
+            right_rows = bottom_cols = 0;
         }
     }
     bool in_band(int64_t i, int64_t j) const { return j + p >= i && i + q >= j; }
@@ -162,37 +188,95 @@ struct BandFactor {
         if (!cyclic) throw std::out_of_range("entry outside the band");
         if (j > i + q) {
             if (j < n - p) throw std::out_of_range("entry outside band and corners");
+            right_rows = std::max(right_rows, i + 1);
             return rgt(i, j);
         }
         if (i < n - q) throw std::out_of_range("entry outside band and corners");
+        bottom_cols = std::max(bottom_cols, j + 1);
         return bot(i, j);
     }
 
-    // Right-looking elimination; every entry receives its updates in ascending k,
-    // like BandLU.hpp:103-118 / :159-213.
-    void factor() {
-        for (int64_t k = 0; k + 1 < n; ++k) {
-            const R piv = main(k, k);
-            const int64_t r_end = std::min<int64_t>(k + p + 1, n);   // band rows   k+1 .. r_end-1
-            const int64_t c_end = std::min<int64_t>(k + q + 1, n);   // band cols   k+1 .. c_end-1
-            const int64_t rs = cyclic ? std::max<int64_t>(n - q, k + p + 1) : n;  // corner rows rs..n-1
-            const int64_t cs = cyclic ? std::max<int64_t>(n - p, k + q + 1) : n;  // corner cols cs..n-1
-            for (int64_t i = k + 1; i < r_end; ++i) main(i, k) /= piv;
+    // One elimination step (pivot k), right-looking; every entry receives its updates in
+    // ascending k, like BandLU.hpp:103-118 / :159-213.
+    void step(int64_t k) {
+        const R piv = main(k, k);
+        const int64_t r_end = std::min<int64_t>(k + p + 1, n);   // band rows   k+1 .. r_end-1
+        const int64_t c_end = std::min<int64_t>(k + q + 1, n);   // band cols   k+1 .. c_end-1
+        const int64_t rs = cyclic ? std::max<int64_t>(n - q, k + p + 1) : n;  // corner rows rs..n-1
+        const int64_t cs = cyclic ? std::max<int64_t>(n - p, k + q + 1) : n;  // corner cols cs..n-1
+        for (int64_t i = k + 1; i < r_end; ++i) main(i, k) /= piv;
+        if (k < bottom_cols)
             for (int64_t i = rs; i < n; ++i) bot(i, k) /= piv;
-            for (int64_t i = k + 1; i < r_end; ++i) {
-                const R l = main(i, k);
-                for (int64_t j = k + 1; j < c_end; ++j) main(i, j) -= l * main(k, j);
+        for (int64_t i = k + 1; i < r_end; ++i) {
+            const R l = main(i, k);
+            for (int64_t j = k + 1; j < c_end; ++j) main(i, j) -= l * main(k, j);
+            if (k < right_rows)
                 for (int64_t j = cs; j < n; ++j) {
                     const R u = rgt(k, j);
                     if (u != R(0)) at(i, j) -= l * u;
                 }
+        }
+        for (int64_t i = rs; i < n && k < bottom_cols; ++i) {
+            const R l = bot(i, k);
+            if (l == R(0)) continue;
+            for (int64_t j = k + 1; j < c_end; ++j) at(i, j) -= l * main(k, j);
+            for (int64_t j = cs; j < n; ++j) main(i, j) -= l * rgt(k, j);
+        }
+    }
+
+    // Elimination with a fast-forward through the translation-invariant interior of a
+    // uniform axis.  Once (a) the rows ahead are bit-identical shifted copies of one another
+    // in the ORIGINAL matrix, (b) the corner strips no longer carry anything into the band
+    // (their entries in row/column k are exactly zero) and (c) the working state after step k
+    // equals the state after step k-1 shifted by one row, every later step in that run
+    // reproduces the same bits -- floating point is deterministic -- so its results are
+    // copied instead of recomputed.  The factors are bit-identical to the plain loop's
+    // (tests/test_abi.py checks that bit for bit); a 2^24-row axis costs O(1000)
+    // real steps instead of 1.7e7.
+    void factor() {
+        const int w = p + q + 1;
+        // same[i]: original band row i is a shifted copy of row i-1 and neither touches a corner strip
+        std::vector<unsigned char> same(static_cast<size_t>(n), 0);
+        if (n > 4 * (p + q + 2)) {
+            for (int64_t i = p + 1; i < n - q - 1; ++i) {
+                bool eq = true;
+                for (int c = 0; c < w && eq; ++c) eq = band[i * w + c] == band[(i - 1) * w + c];
+                same[i] = eq;
             }
-            for (int64_t i = rs; i < n; ++i) {
-                const R l = bot(i, k);
-                if (l == R(0)) continue;
-                for (int64_t j = k + 1; j < c_end; ++j) at(i, j) -= l * main(k, j);
-                for (int64_t j = cs; j < n; ++j) main(i, j) -= l * rgt(k, j);
+        }
+        std::vector<R> prev_state(static_cast<size_t>(p + 1) * w), cur_state(prev_state.size());
+        bool have_prev = false;
+        int64_t k = 0;
+        while (k + 1 < n) {
+            step(k);
+            bool can = k + p + 1 < n && same[k + p + 1];
+            if (can && cyclic) {
+                if (k < right_rows)
+                    for (int64_t j = std::max<int64_t>(n - p, k + q + 1); j < n && can; ++j) can = rgt(k, j) == R(0);
+                if (k < bottom_cols)
+                    for (int64_t i = std::max<int64_t>(n - q, k + p + 1); i < n && can; ++i) can = bot(i, k) == R(0);
             }
+            if (!can) { have_prev = false; ++k; continue; }
+            for (int r = 0; r <= p; ++r)
+                for (int c = 0; c < w; ++c) cur_state[r * w + c] = band[(k + r) * w + c];
+            if (have_prev && cur_state == prev_state) {
+                // run length: original rows k+p+1 .. stay shift-identical
+                int64_t last = k + p + 1;
+                while (last + 1 < n && same[last + 1]) ++last;
+                const int64_t k_end = last - p;  // steps k+1 .. k_end behave like step k
+                if (k_end > k + 1) {
+                    for (int64_t r = k + 1; r <= k_end; ++r)
+                        for (int c = 0; c < w; ++c) band[r * w + c] = cur_state[c];
+                    for (int r = 1; r <= p; ++r)
+                        for (int c = 0; c < w; ++c) band[(k_end + r) * w + c] = cur_state[r * w + c];
+                    k = k_end + 1;
+                    have_prev = false;
+                    continue;
+                }
+            }
+            prev_state.swap(cur_state);
+            have_prev = true;
+            ++k;
         }
     }
 };
@@ -234,10 +318,16 @@ void build_axis_factor(const HostAxis<R>& a, BandFactor<R>& m) {
             a.basis(seg, x, bsv);
         }
         const int cnt = a.periodic ? (O | 1) : O == 1 ? 1 : (a.uniform && internal) ? (O | 1) : O + 1;
-        for (int j = 0; j < cnt; ++j) {
-            const int64_t row = (i + (a.periodic ? bw : 0)) % N;
-            const int64_t col = (seg - O + j) % N;
-            m.at(row, col) = bsv[j];
+        const int64_t row0 = i + (a.periodic ? bw : 0), col0 = seg - O;
+        if (row0 < N && col0 + cnt <= N && col0 + bw >= row0 && row0 + bw >= col0 + cnt - 1) {
+            // no wrap, whole row inside the band: the common case on long axes
+            for (int j = 0; j < cnt; ++j) m.main(row0, col0 + j) = bsv[j];
+        } else {
+            for (int j = 0; j < cnt; ++j) {
+                const int64_t row = row0 % N;
+                const int64_t col = (col0 + j) % N;
+                m.at(row, col) = bsv[j];
+            }
         }
     }
     m.factor();

@@ -62,14 +62,44 @@ def _host_factor(L, order, per, n, lo, hi, coords=None):
     return (P,) + tuple(arrs)
 
 
+def _row_form_from_oracle(o, n, P, per):
+    """The oracle's diagonal-major LU store (BandMatrix.hpp:50-60, :122-146) in the row form the
+    kernels consume."""
+    band, right, bottom = o.lu(0)
+    p = band.shape[1] // 2
+    Lr = np.zeros((n, max(P, 1))); U = np.zeros_like(Lr)
+    dg = band[:, p].copy()
+    i = np.arange(n)
+    for m in range(P):
+        jl = i - P + m
+        ok = jl >= 0
+        Lr[ok, m] = band[jl[ok], (i + p - jl)[ok]]
+        ju = i + 1 + m
+        ok = ju < n
+        U[ok, m] = band[ju[ok], (i + p - ju)[ok]]
+    B = np.zeros_like(Lr); R = np.zeros_like(Lr)
+    if per and P > 0:
+        for c in range(p):            # right strip: column j = n-p+c, rows i < j-p
+            j = n - p + c
+            rows = np.arange(0, j - p)
+            R[rows, j - (n - P)] = right[rows, j + p - n]
+        for r in range(p):            # bottom strip: row ii = n-p+r, columns j < ii-p
+            ii = n - p + r
+            cols = np.arange(0, ii - p)
+            B[cols, ii - (n - P)] = bottom[cols, ii + p - n]
+    return Lr, U, dg, B, R
+
+
 @pytest.mark.parametrize("order", range(6))
 @pytest.mark.parametrize("per", [0, 1])
 def test_host_template_construction_matches_oracle(lib_built, order, per):
+    """Knots, ranges and LU factors bit-identical to the oracle's -- including long uniform axes,
+    where the host factorisation fast-forwards through its steady state."""
     L = lib_built.lib()
     rng = np.random.default_rng(order * 2 + per)
-    for n in (7, 12, 33, 64):
+    for n in (7, 12, 33, 64, 1500, 4099):
         for nonuni in (0, 1):
-            if nonuni and order == 0 and not per:
+            if nonuni and ((order == 0 and not per) or n > 64):
                 continue
             lo, hi = -1.3, 2.9
             coords = None
@@ -79,24 +109,10 @@ def test_host_template_construction_matches_oracle(lib_built, order, per):
             k, r = _host_knots(L, order, per, n, lo, hi, coords)
             assert np.array_equal(k, o.knots(0)) and r == o.range(0)
             P, Lr, U, dg, B, R = _host_factor(L, order, per, n, lo, hi, coords)
-            band, right, bottom = o.lu(0)
-            p = band.shape[1] // 2
-            assert P == p
-            for i in range(n):
-                assert dg[i] == band[i, p]
-                for m in range(P):
-                    jl, ju = i - P + m, i + 1 + m
-                    if jl >= 0:
-                        assert Lr[i, m] == band[jl, i + p - jl]
-                    if ju < n:
-                        assert U[i, m] == band[ju, i + p - ju]
-            if per and P > 0:
-                for i in range(n):
-                    for j in range(n):
-                        if j > i + p and j >= n - p:
-                            assert R[i, j - (n - P)] == right[i, j + p - n]
-                        if i > j + p and i >= n - p:
-                            assert B[j, i - (n - P)] == bottom[j, i + p - n]
+            eL, eU, edg, eB, eR = _row_form_from_oracle(o, n, P, per)
+            assert P == o.lu(0)[0].shape[1] // 2
+            for got, exp, name in ((Lr, eL, "L"), (U, eU, "U"), (dg, edg, "diag"), (B, eB, "bottom"), (R, eR, "right")):
+                assert np.array_equal(got, exp), (name, order, per, n, nonuni)
 
 
 def test_invalid_arguments_reported(lib_built):
