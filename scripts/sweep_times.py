@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bsplineinterpolation_b200 as B
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 512
-t = B.InterpolationFunctionTemplate(3, (n, n, n), [(0.0, 1.0)] * 3)
+per = [len(sys.argv) > 2 and sys.argv[2] == "periodic"] * 3
+t = B.InterpolationFunctionTemplate(3, (n, n, n), [(0.0, 1.0)] * 3, per)
 w = torch.rand((n, n, n), dtype=torch.float64, device="cuda")
 def tm(fn, reps=5):
     fn(); torch.cuda.synchronize(); ts = []
