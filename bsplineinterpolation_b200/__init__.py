@@ -4,9 +4,11 @@ control-point solve.  The numerical work lives in csrc/ (hand-written CUDA
 behind the C ABI of include/bspline_b200.h); this package is the thin host
 mirror of the reference API used by tests and benchmarks."""
 from ._capi import BsplError, lib  # noqa: F401
-from .interpolation import (BSpline, InterpolationFunction, InterpolationFunctionTemplate,  # noqa: F401
+from .interpolation import (BSpline, InterpolationFunction, InterpolationFunction1D,  # noqa: F401
+                            InterpolationFunctionTemplate, InterpolationFunctionTemplate1D,
                             band_solve, last_kernel_ms, launch_count, reset_launch_count,
                             set_eval_path)
 
-__all__ = ["InterpolationFunction", "InterpolationFunctionTemplate", "BSpline", "band_solve", "lib",
+__all__ = ["InterpolationFunction", "InterpolationFunctionTemplate", "InterpolationFunction1D",
+           "InterpolationFunctionTemplate1D", "BSpline", "band_solve", "lib",
            "BsplError", "launch_count", "reset_launch_count", "last_kernel_ms", "set_eval_path"]

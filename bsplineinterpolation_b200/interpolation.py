@@ -303,6 +303,24 @@ class InterpolationFunctionTemplate:
         return InterpolationFunction(_handle=out)
 
 
+def InterpolationFunction1D(f, order=3, x_range=None, periodicity=False, dtype=np.float64, device=0):
+    """1-D convenience (Interpolation.hpp:509-540): default x range [0, N-1], or [0, N] when
+    periodic (INTP_PERIODIC_NO_DUMMY_POINT)."""
+    f = np.asarray(f) if not _is_device(f) else f
+    n = f.shape[0]
+    if x_range is None:
+        x_range = (0.0, float(n - (0 if periodicity else 1)))
+    return InterpolationFunction(order, f, [x_range], [bool(periodicity)], dtype=dtype, device=device)
+
+
+def InterpolationFunctionTemplate1D(f_length, order=3, x_range=None, periodicity=False, dtype=np.float64, device=0):
+    """1-D template (InterpolationTemplate.hpp:583-604): default x range [0, f_length - 1]."""
+    if x_range is None:
+        x_range = (0.0, float(f_length - 1))
+    return InterpolationFunctionTemplate(order, (int(f_length),), [x_range], [bool(periodicity)], dtype=dtype,
+                                         device=device)
+
+
 class BSpline:
     @staticmethod
     def from_knots(order, periodicity, knots, control_points, dtype=np.float64, device=0):

@@ -361,3 +361,66 @@ def test_many_fields_cfg5_shape(pkg):
         o = OracleSpline(3, shape, [0, 0], lo=[0, 0], hi=[1, 1], f=fields[k])
         assert np.array_equal(fn.control_points(k), o.control_points())
         _close(allv[k], o.eval(pts))
+
+
+def test_baseline_cfg1_2d_cubic_1024(pkg):
+    """BASELINE configs[0]: 2-D cubic 1024x1024 mesh, 1M random queries, against the oracle."""
+    rng = np.random.default_rng(12345)
+    shape = (1024, 1024)
+    f = smooth_field(shape, rng)
+    o = OracleSpline(3, shape, [0, 0], lo=[0, 0], hi=[1, 1], f=f, nthreads=8)
+    fn = pkg.InterpolationFunction(3, f, [(0.0, 1.0), (0.0, 1.0)])
+    assert np.array_equal(fn.control_points(), o.control_points())
+    pts = rng.uniform(0, 1, (1 << 20, 2))
+    assert np.array_equal(fn.locate(pts), o.spans(pts))
+    _close(fn(pts), o.eval(pts, 8))
+    _close(fn.derivative(pts, [1, 0]), o.deriv(pts, [1, 0], 8))
+
+
+def test_baseline_cfg2_1d_quintic_periodic_long(pkg):
+    """BASELINE configs[1] scaled to 2^21 mesh points (the oracle's serial LU bounds the size):
+    1-D order-5 periodic, value + first derivative, chunk-parallel solve.  A long axis is where
+    rounded knot values matter most: the tolerance is still 1e-12."""
+    rng = np.random.default_rng(7)
+    n = 1 << 21
+    f = np.sin(np.arange(n) * (14 * np.pi / n)) + 0.1 * rng.standard_normal(n)
+    o = OracleSpline(5, (n,), [1], lo=[0.0], hi=[1.0], f=f)
+    fn = pkg.InterpolationFunction(5, f, [(0.0, 1.0)], [True])
+    c, ref = fn.control_points(), o.control_points()
+    assert np.abs(c - ref).max() <= 1e-13 * np.abs(ref).max()
+    pts = rng.uniform(-0.5, 1.5, 1 << 20)  # includes wrapped queries
+    assert np.array_equal(fn.locate(pts)[:, 0], o.spans(pts)[:, 0])
+    vg = fn.value_grad(pts)
+    _close(vg[:, 0], o.eval(pts, 8))
+    _close(vg[:, 1], o.deriv(pts, [1], 8))
+
+
+def test_baseline_cfg3_3d_cubic_256_sample(pkg):
+    """BASELINE configs[2] at full mesh size: 256^3 cubic, value + gradient through the binned/TMA
+    path on 2^22 queries; a 2^17-query sample is checked against the oracle, the whole batch
+    against the direct path, and the spline must reproduce its data at the mesh nodes."""
+    import torch
+    rng = np.random.default_rng(99)
+    shape = (256, 256, 256)
+    f = smooth_field(shape, rng)
+    fn = pkg.InterpolationFunction(3, torch.from_numpy(f).cuda(), [(0.0, 1.0)] * 3)
+    o = OracleSpline(3, shape, [0, 0, 0], lo=[0, 0, 0], hi=[1, 1, 1], f=f, nthreads=8)
+    assert np.array_equal(fn.control_points(), o.control_points())
+    pts = rng.uniform(0, 1, (1 << 22, 3))
+    d = torch.from_numpy(pts).cuda()
+    vg = fn.value_grad(d).cpu().numpy()           # auto -> binned (Q >= 256 * tiles)
+    try:
+        pkg.set_eval_path("direct")
+        vd = fn.value_grad(d).cpu().numpy()
+    finally:
+        pkg.set_eval_path("auto")
+    assert np.abs(vg - vd).max() <= 1e-13 * np.abs(vd).max()
+    s = slice(0, 1 << 17)
+    assert np.array_equal(fn.locate(pts[s]), o.spans(pts[s]))
+    _close(vg[s, 0], o.eval(pts[s], 8))
+    for k in range(3):
+        dv = [0, 0, 0]; dv[k] = 1
+        _close(vg[s, 1 + k], o.deriv(pts[s], dv, 8))
+    idx = rng.integers(0, 256, size=(20000, 3))
+    nodes = idx / 255.0
+    assert np.abs(fn(nodes) - f[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f).max()
