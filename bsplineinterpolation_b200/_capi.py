@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbspline_b200.so")
+LIB_PATH = os.environ.get("BSPL_B200_LIB", os.path.join(HERE, "libbspline_b200.so"))
 
 OK, ERR_INVALID, ERR_CUDA, ERR_DOMAIN, ERR_ALLOC, ERR_UNSUPPORTED = range(6)
 F64, F32 = 0, 1
