@@ -122,10 +122,13 @@ class ShardedSolve3D:
         """f_slab: CUDA tensor [n0_loc, n1, n2], this rank's axis-0 slab of the mesh.
         Returns the control points as a slab of axis 1, [n0, n1_loc, n2] (or of axis 0)."""
         n0, n1, n2 = self.shape
-        w = self._shift(self._shift(f_slab, 2), 1).contiguous().clone()
-        n0_loc = w.shape[0]
+        n0_loc = f_slab.shape[0]
         t = self.template
-        t.sweep_axis(2, w, (1, n0_loc, n1), (0, n1 * n2, n2), 1)
+        # A thread-per-line sweep along the contiguous axis cannot be coalesced: sweep axis 2 in a
+        # transposed copy [n0_loc][n2][n1] (lines of stride n1), then transpose back for axis 1.
+        wt = self._shift(self._shift(f_slab, 2), 1).transpose(1, 2).contiguous()
+        t.sweep_axis(2, wt, (1, n0_loc, n1), (0, n1 * n2, 1), n1)
+        w = wt.transpose(1, 2).contiguous()
         t.sweep_axis(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2)
         y = reshard_axis0_to_axis1(w, n0, self.group)
         y = self._shift(y, 0).contiguous()
