@@ -431,3 +431,40 @@ def test_baseline_cfg3_3d_cubic_256_sample(pkg):
     idx = rng.integers(0, 256, size=(20000, 3))
     nodes = idx / 255.0
     assert np.abs(fn(nodes) - f[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f).max()
+
+
+def test_vector_valued_circle_as_two_fields(pkg):
+    """interpolation-test.cpp:674-703 (T = Vec<2,float>, U = float): a closed curve interpolated
+    componentwise; here the components are the fields of one handle sharing one query set."""
+    n = 31
+    theta = 2.0 * np.pi * np.arange(n) / n
+    pts_xy = np.stack([np.cos(theta), np.sin(theta)]).astype(np.float32)  # [2 fields][n]
+    t = pkg.InterpolationFunctionTemplate(3, (n,), [(0.0, float(n))], [True], dtype=np.float32)
+    circle = t.interpolate(pts_xy)
+    q = (np.arange(1024, dtype=np.float32) * (n / 1024.0)).reshape(-1, 1)  # parameter in mesh units
+    xy = circle.evaluate_fields(q)
+    err = np.abs(np.hypot(xy[0], xy[1]) - 1.0).mean()
+    assert err < 1e-5  # the reference's bound, :697
+
+
+def test_concurrent_host_threads(pkg):
+    """Evaluation is re-entrant: several host threads on one handle (host-pointer path is serialised
+    by the staging pipe, device results must still be exact)."""
+    import threading
+    rng = np.random.default_rng(4)
+    shape = (20, 24, 28)
+    f = smooth_field(shape, rng)
+    fn = pkg.InterpolationFunction(3, f, [(0.0, 1.0)] * 3)
+    pts = [rng.uniform(0, 1, (30000, 3)) for _ in range(4)]
+    want = [fn.value_grad(p) for p in pts]
+    got = [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            got[i] = fn.value_grad(pts[i])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for w, g in zip(want, got):
+        assert np.array_equal(w, g)
