@@ -165,6 +165,29 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(local):
+    """Plumbing for the end-to-end leg: run this rank (and first-touch its pinned buffers) on the
+    NUMA node its GPU hangs off.  Returns the node, or None when the platform does not say."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -178,6 +201,7 @@ def run_gpu(args):
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -309,7 +333,8 @@ def run_gpu(args):
                          "stream_only_frac": q * B_STREAM / (kern_ms * 1e-3) / 1e9 / hbm_peak},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": qe * 24, "d2h_bytes_per_step": qe * 32,
-                    "queries_per_gpu": qe, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err},
+                    "queries_per_gpu": qe, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err,
+                    "numa_node_rank0": numa_node},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "solve": solve,

@@ -23,6 +23,12 @@ SIGNATURES = {
     "bspl_template_interpolate": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
     "bspl_template_interpolate_into": (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, _vp]),
     "bspl_template_sweep_axis": (C.c_int, [_vp, C.c_int, _vp, _i64p, _i64p, C.c_int64, _vp]),
+    "bspl_template_sweep_axis_exchange": (C.c_int, [_vp, C.c_int, _vp, _i64p, _i64p, C.c_int64, C.c_int, _i64p,
+                                                    _vpp, _ip, _i64p, _i64p, _vp]),
+    "bspl_ipc_alloc": (C.c_int, [C.c_int, C.c_int64, _vpp, C.POINTER(C.c_ubyte)]),
+    "bspl_ipc_open": (C.c_int, [C.c_int, C.POINTER(C.c_ubyte), _vpp]),
+    "bspl_ipc_close": (C.c_int, [C.c_int, _vp]),
+    "bspl_ipc_free": (C.c_int, [C.c_int, _vp]),
     "bspl_template_function_from_ctrl": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
     "bspl_function_from_control_points": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p, _ip, C.POINTER(_dp),
                                                     _i64p, _vp, C.c_int64, C.c_int, _vpp]),

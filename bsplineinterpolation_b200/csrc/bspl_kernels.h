@@ -118,6 +118,23 @@ cudaError_t launch_fill_ghosts(const GhostGeom& g, R* data, cudaStream_t s);
 template <typename R>
 cudaError_t launch_unpad_copy(const CopyGeom& g, const R* src_padded, R* dst_compact, cudaStream_t s);
 
+// Sweep fused with the re-shard of the slab-sharded multi-GPU solve: the forward pass runs in
+// place on the local slab, the backward pass stores every solved row straight into the buffer of
+// the rank that owns it after the exchange (peer-mapped device memory, NVLink stores) -- no pack,
+// no separate all-to-all, no unpack.
+constexpr int kMaxPeers = 8;
+template <typename R>
+struct ExchangeDest {
+    int n_ranks;
+    int split[kMaxPeers + 1];   // rows [split[r], split[r+1]) of every line belong to rank r
+    R* base[kMaxPeers];         // rank r's buffer, already offset to this rank's block in it
+    long long ms[kMaxPeers][3]; // strides of the three outer line indices in rank r's buffer
+    long long ls[kMaxPeers];    // stride between consecutive rows in rank r's buffer
+};
+template <typename R>
+cudaError_t launch_sweep_exchange(const AxisLU<R>& lu, const SweepGeom& g, R* data, const ExchangeDest<R>& dest,
+                                  cudaStream_t s);
+
 // Batched transpose of the last two axes through shared memory:
 //   dst[(b0, b1), rot_q(q), rot_p(p)] = src[(b0, b1), p, q]     (src q-contiguous, dst p-contiguous)
 // with optional rotation of every index by +shift (mod extent) on the destination side.

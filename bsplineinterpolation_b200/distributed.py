@@ -99,6 +99,19 @@ def reshard_axis1_to_axis0(local, n1, group=None):
     return out
 
 
+class _DevicePtr:
+    """A raw device allocation seen as a float64 CUDA array (plumbing: lets torch view memory that
+    the library allocated for IPC)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f8",
+                                         "data": (int(ptr), False), "version": 3, "strides": None}
+
+    def tensor(self, device):
+        import torch
+        return torch.as_tensor(self, device=torch.device("cuda", device))
+
+
 class ShardedSolve3D:
     """Slab-sharded control-point solve of ONE 3-D field over the ranks of `group`."""
 
@@ -135,6 +148,90 @@ class ShardedSolve3D:
         n1_loc = y.shape[1]
         t.sweep_axis(0, y, (1, 1, n1_loc * n2), (0, 0, 1), n1_loc * n2)
         return reshard_axis1_to_axis0(y, n1, self.group) if back_to_axis0 else y
+
+    # ---- fused exchange: the last local sweep stores straight into the owners' buffers ----
+    def enable_fused_exchange(self):
+        """Allocate this rank's receive buffer [n0][n1_loc][n2] (bspl_ipc_alloc) and map every
+        peer's buffer for access from this rank's GPU (bspl_ipc_open).  Collective."""
+        import ctypes as C
+        import torch
+        import torch.distributed as dist
+        from ._capi import check, lib
+        rank, world = _rank_world(self.group)
+        n0, n1, n2 = self.shape
+        s1 = shard_sizes(n1, world)
+        dev = torch.cuda.current_device()
+        self._dev = dev
+        handle = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        check(lib().bspl_ipc_alloc(dev, n0 * s1[rank] * n2 * 8, C.byref(ptr), handle))
+        self._own_ptr = ptr.value
+        self._recv = _DevicePtr(ptr.value, (n0, s1[rank], n2)).tensor(dev)
+        self._opened = []
+        if world == 1:
+            self._peers = [self._recv]
+            return
+        everyone = [None] * world
+        dist.all_gather_object(everyone, bytes(handle), group=self.group)
+        self._peers = []
+        for r in range(world):
+            if r == rank:
+                self._peers.append(self._recv)
+                continue
+            h = (C.c_ubyte * 64).from_buffer_copy(everyone[r])
+            p = C.c_void_p()
+            check(lib().bspl_ipc_open(dev, h, C.byref(p)))
+            self._opened.append(p.value)
+            self._peers.append(_DevicePtr(p.value, (n0, s1[r], n2)).tensor(dev))
+
+    def close_fused_exchange(self):
+        """Unmap the peers' buffers, then (after a barrier) free this rank's.  Collective."""
+        import torch
+        import torch.distributed as dist
+        from ._capi import check, lib
+        torch.cuda.synchronize()
+        self._peers = []
+        for p in getattr(self, "_opened", []):
+            check(lib().bspl_ipc_close(self._dev, p))
+        self._opened = []
+        if _rank_world(self.group)[1] > 1:
+            dist.barrier(group=self.group)
+        if getattr(self, "_own_ptr", None):
+            self._recv = None
+            check(lib().bspl_ipc_free(self._dev, self._own_ptr))
+            self._own_ptr = None
+
+    def solve_fused(self, f_slab):
+        """As solve(), but the axis-1 sweep writes its solved rows directly into the receive buffers
+        of their owners over NVLink (bspl_template_sweep_axis_exchange): no pack, no NCCL
+        all-to-all, no unpack.  Returns this rank's slab of axis 1, [n0, n1_loc, n2]; the buffer
+        is reused by the next call."""
+        import torch
+        import torch.distributed as dist
+        rank, world = _rank_world(self.group)
+        n0, n1, n2 = self.shape
+        n0_loc = f_slab.shape[0]
+        x0 = shard_range(n0, rank, world)[0]
+        s1 = shard_sizes(n1, world)
+        t = self.template
+        wt = self._shift(self._shift(f_slab, 2), 1).transpose(1, 2).contiguous()
+        t.sweep_axis(2, wt, (1, n0_loc, n1), (0, n1 * n2, 1), n1)
+        w = wt.transpose(1, 2).contiguous()
+        if world > 1:
+            dist.barrier(group=self.group)  # every rank has consumed its previous result
+        split = np.concatenate([[0], np.cumsum(s1)])
+        t.sweep_axis_exchange(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2, split,
+                              [self._peers[r][x0:] for r in range(world)], [-1] * world,
+                              [(0, s1[r] * n2, 1) for r in range(world)], [n2] * world)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=self.group)  # every block of my buffer has arrived
+        y = self._recv
+        if self.periodicity[0] and self.order // 2:
+            y = self._shift(y, 0).contiguous()
+        n1_loc = y.shape[1]
+        t.sweep_axis(0, y, (1, 1, n1_loc * n2), (0, 0, 1), n1_loc * n2)
+        return y
 
     def gather_function(self, ctrl_axis1_slab):
         """All-gather the solved slabs and build a replicated InterpolationFunction."""

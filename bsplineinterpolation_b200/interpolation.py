@@ -295,6 +295,25 @@ class InterpolationFunctionTemplate:
                                              int(line_stride), C.c_void_p(sp)))
         return data
 
+    def sweep_axis_exchange(self, axis, data, outer_sizes, outer_strides, line_stride, split, peers,
+                            peer_devices, peer_outer_strides, peer_line_strides, stream=None):
+        """sweep_axis whose backward pass stores each solved row into the (peer-mapped) tensor of
+        the rank that owns it; see bspl_template_sweep_axis_exchange.  `peers[r]` is a CUDA
+        tensor view whose first element is where this rank's block starts in rank r's buffer."""
+        import torch
+        n_ranks = len(peers)
+        _a, m = _i64(list(outer_sizes))
+        _b, ms = _i64(list(outer_strides))
+        _c, sp_ = _i64(list(split))
+        bases = (C.c_void_p * n_ranks)(*[C.c_void_p(p.data_ptr()) for p in peers])
+        _d, devs = _i32(list(peer_devices))
+        _e, pms = _i64([v for row in peer_outer_strides for v in row])
+        _f, pls = _i64(list(peer_line_strides))
+        sp = stream if stream is not None else torch.cuda.current_stream(data.device).cuda_stream
+        check(lib().bspl_template_sweep_axis_exchange(self._h, int(axis), C.c_void_p(data.data_ptr()), m, ms,
+                                                      int(line_stride), n_ranks, sp_, bases, devs, pms, pls,
+                                                      C.c_void_p(sp)))
+
     def function_from_control_points(self, ctrl):
         """Wrap solved plain control points (numpy or CUDA tensor, leading field axis optional)."""
         keep, ptr, n_fields, dev, sp = self._mesh_ptr(ctrl)

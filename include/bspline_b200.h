@@ -88,6 +88,27 @@ int bspl_template_interpolate_into(const bspl_template* t, bspl_function* fn, co
  * (sweep local axes, all-to-all, sweep the remaining axis). */
 int bspl_template_sweep_axis(const bspl_template* t, int axis, void* data, const int64_t* m,
                              const int64_t* ms, int64_t line_stride, void* stream);
+/* bspl_template_sweep_axis fused with the re-shard of the slab-sharded solve: the forward
+ * substitution runs in place on `data`; the backward substitution stores row j of every line
+ * into the buffer of the rank that owns it, rank r owning rows [split[r], split[r+1]).  The
+ * element (i0, i1, i2, j) lands at peer_base[r] + i0*peer_ms[3r] + i1*peer_ms[3r+1] +
+ * i2*peer_ms[3r+2] + (j - split[r]) * peer_ls[r].  peer_base[r] is device memory of GPU
+ * peer_device[r] mapped into this process (CUDA IPC); peer access is enabled on demand.
+ * `data` holds the forward-substituted values afterwards and is scratch.  The caller
+ * synchronises the ranks before reading its own buffer.  n_ranks <= 8. */
+int bspl_template_sweep_axis_exchange(const bspl_template* t, int axis, void* data, const int64_t* m,
+                                      const int64_t* ms, int64_t line_stride, int n_ranks,
+                                      const int64_t* split, void* const* peer_base,
+                                      const int* peer_device, const int64_t* peer_ms,
+                                      const int64_t* peer_ls, void* stream);
+/* Device buffers shareable between the ranks of one node (CUDA IPC), for the exchange above:
+ * alloc returns device memory of `device` and a 64-byte handle to send to the peers; open maps
+ * a peer's buffer for access from kernels running on `device` (the ACCESSING device).  Close
+ * every opened mapping before the owner frees the buffer. */
+int bspl_ipc_alloc(int device, int64_t bytes, void** dptr, unsigned char handle_out[64]);
+int bspl_ipc_open(int device, const unsigned char handle[64], void** dptr);
+int bspl_ipc_close(int device, void* dptr);
+int bspl_ipc_free(int device, void* dptr);
 /* Wrap already-solved plain control points ([n_fields][n0]...[nD-1], host or device) into
  * a function of this template (load_ctrlPts, BSpline.hpp:229-242). */
 int bspl_template_function_from_ctrl(const bspl_template* t, const void* ctrl, int64_t n_fields,

@@ -26,6 +26,9 @@ def test_staged_solve_single_rank(lib_built, order, periodic):
     o = OracleSpline(order, shape, periodic, lo=[r[0] for r in ranges], hi=[r[1] for r in ranges], f=f)
     assert np.array_equal(ctrl.cpu().numpy(), o.control_points())
     fn = sh.gather_function(ctrl)
+    sh.enable_fused_exchange()
+    assert np.array_equal(sh.solve_fused(torch.from_numpy(f).cuda()).cpu().numpy(), o.control_points())
+    sh.close_fused_exchange()
     pts = np.array([r[0] for r in ranges]) + rng.uniform(0, 1, (2000, 3)) * np.array([r[1] - r[0] for r in ranges])
     ref = o.eval(pts)
     assert np.abs(fn(pts) - ref).max() <= 1e-12 * np.abs(ref).max()
@@ -61,6 +64,13 @@ def _worker(rank, world, port, out_dir):
         ok = np.array_equal(fn.control_points(), o.control_points())
         back = sh.solve(torch.from_numpy(f[b:e]).cuda(rank), back_to_axis0=True)
         ok = ok and np.array_equal(back.cpu().numpy(), o.control_points()[b:e])
+        # fused sweep + exchange over peer memory
+        sh.enable_fused_exchange()
+        b1, e1 = shard_range(shape[1], rank, world)
+        for _ in range(2):
+            fused = sh.solve_fused(torch.from_numpy(f[b:e]).cuda(rank))
+            ok = ok and np.array_equal(fused.cpu().numpy(), o.control_points()[:, b1:e1, :])
+        sh.close_fused_exchange()
         with open(os.path.join(out_dir, "r%d" % rank), "w") as fh:
             fh.write("%d" % ok)
     finally:
