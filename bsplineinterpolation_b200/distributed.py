@@ -168,6 +168,7 @@ class ShardedSolve3D:
         self._own_ptr = ptr.value
         self._recv = _DevicePtr(ptr.value, (n0, s1[rank], n2)).tensor(dev)
         self._opened = []
+        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
         if world == 1:
             self._peers = [self._recv]
             return
@@ -218,14 +219,16 @@ class ShardedSolve3D:
         t.sweep_axis(2, wt, (1, n0_loc, n1), (0, n1 * n2, 1), n1)
         w = wt.transpose(1, 2).contiguous()
         if world > 1:
-            dist.barrier(group=self.group)  # every rank has consumed its previous result
+            # stream-ordered barrier (a one-element NCCL all-reduce, no host synchronisation): every
+            # rank has consumed its previous result before anyone overwrites the buffers
+            dist.all_reduce(self._flag, group=self.group)
         split = np.concatenate([[0], np.cumsum(s1)])
         t.sweep_axis_exchange(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2, split,
                               [self._peers[r][x0:] for r in range(world)], [-1] * world,
                               [(0, s1[r] * n2, 1) for r in range(world)], [n2] * world)
-        torch.cuda.synchronize()
         if world > 1:
-            dist.barrier(group=self.group)  # every block of my buffer has arrived
+            # every rank's exchange kernel has completed (its peer stores are visible at kernel end)
+            dist.all_reduce(self._flag, group=self.group)
         y = self._recv
         if self.periodicity[0] and self.order // 2:
             y = self._shift(y, 0).contiguous()
