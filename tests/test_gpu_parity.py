@@ -468,3 +468,30 @@ def test_concurrent_host_threads(pkg):
     [t.join() for t in th]
     for w, g in zip(want, got):
         assert np.array_equal(w, g)
+
+
+def test_non_finite_queries_do_not_disturb_the_batch(pkg):
+    """NaN / inf coordinates must neither crash a kernel nor change the results of the other
+    queries of the batch (both evaluation paths)."""
+    import torch
+    rng = np.random.default_rng(17)
+    shape = (40, 36, 44)
+    f = smooth_field(shape, rng)
+    for periodic in ((False, False, False), (True, True, True)):
+        fn = pkg.InterpolationFunction(3, f, [(0.0, 1.0)] * 3, periodic)
+        pts = rng.uniform(0, 1, (50000, 3))
+        bad = pts.copy()
+        rows = rng.choice(len(pts), 500, replace=False)
+        bad[rows[:200], 0] = np.nan
+        bad[rows[200:350], 1] = np.inf
+        bad[rows[350:], 2] = -np.inf
+        good = np.ones(len(pts), dtype=bool); good[rows] = False
+        for path in ("direct", "binned"):
+            try:
+                pkg.set_eval_path(path)
+                ref = fn.value_grad(torch.from_numpy(pts).cuda()).cpu().numpy()
+                got = fn.value_grad(torch.from_numpy(bad).cuda()).cpu().numpy()
+            finally:
+                pkg.set_eval_path("auto")
+            assert np.array_equal(got[good], ref[good])
+            assert np.isnan(got[rows[:200], 0]).all()
