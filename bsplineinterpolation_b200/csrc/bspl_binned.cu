@@ -404,7 +404,7 @@ EncodeTiledFn encode_tiled() {
 }
 
 template <typename R, int O>
-cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s) {
+cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, int phases, cudaStream_t s) {
     constexpr int T = tile_edge<O>();
     constexpr int BE = brick_edge<O>();
     constexpr int BP = brick_pitch<R, O>();
@@ -441,15 +441,24 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStr
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
-    cudaError_t e = cudaMemsetAsync(sc.counts, 0, sizeof(uint32_t) * n_bins, s);
+    cudaError_t e = cudaSuccess;
+    if (phases & kBinnedSort) {
+        e = cudaMemsetAsync(sc.counts, 0, sizeof(uint32_t) * n_bins, s);
+        if (e != cudaSuccess) return e;
+        const int grid = kSMs * 4;
+        key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.tile_of, sc.counts);
+        const int tgrid = (n_tiles * 32 + 255) / 256;
+        tile_totals_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_total);
+        plan_kernel<<<1, 1024, 0, s>>>(sc.tile_total, n_tiles, sc.tile_off, sc.work, sc.n_work, sc.next_item);
+        key_cursor_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_off, sc.cursor);
+        scatter_kernel<R><<<grid, 512, 0, s>>>(sc.tile_of, a.pts, a.q, sc.cursor, static_cast<Rec<R>*>(sc.rec));
+        count_launch(5);
+        e = cudaGetLastError();
+        if (e != cudaSuccess || !(phases & kBinnedEval)) return e;
+    }
+    // the work counter is consumed by every evaluation of a (possibly reused) sorted batch
+    e = cudaMemsetAsync(sc.next_item, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;
-    const int grid = kSMs * 4;
-    key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.tile_of, sc.counts);
-    const int tgrid = (n_tiles * 32 + 255) / 256;
-    tile_totals_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_total);
-    plan_kernel<<<1, 1024, 0, s>>>(sc.tile_total, n_tiles, sc.tile_off, sc.work, sc.n_work, sc.next_item);
-    key_cursor_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_off, sc.cursor);
-    scatter_kernel<R><<<grid, 512, 0, s>>>(sc.tile_of, a.pts, a.q, sc.cursor, static_cast<Rec<R>*>(sc.rec));
 
     ep.rec = static_cast<const Rec<R>*>(sc.rec); ep.out = a.out; ep.work = sc.work; ep.n_work = sc.n_work;
     ep.next_item = sc.next_item;
@@ -466,7 +475,7 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStr
         if (e != cudaSuccess) return e;
         k<<<kSMs * 2, kEvalThreads, smem, s>>>(ep, tmap);
     }
-    count_launch(6);
+    count_launch(1);
     return cudaGetLastError();
 }
 
@@ -515,22 +524,22 @@ int binned_tile_count(const EvalArgs<R>& a) {
 }
 
 template <typename R>
-cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s) {
+cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s, int phases) {
     if (a.q <= 0) return cudaSuccess;
     if (a.dim != 3 || a.n_fields != 1 || a.q >= (1ll << 32)) return cudaErrorInvalidValue;
     switch (a.order) {
-        case 0: return eval_binned_O<R, 0>(a, sc, s);
-        case 1: return eval_binned_O<R, 1>(a, sc, s);
-        case 2: return eval_binned_O<R, 2>(a, sc, s);
-        case 3: return eval_binned_O<R, 3>(a, sc, s);
-        case 4: return eval_binned_O<R, 4>(a, sc, s);
-        case 5: return eval_binned_O<R, 5>(a, sc, s);
+        case 0: return eval_binned_O<R, 0>(a, sc, phases, s);
+        case 1: return eval_binned_O<R, 1>(a, sc, phases, s);
+        case 2: return eval_binned_O<R, 2>(a, sc, phases, s);
+        case 3: return eval_binned_O<R, 3>(a, sc, phases, s);
+        case 4: return eval_binned_O<R, 4>(a, sc, phases, s);
+        case 5: return eval_binned_O<R, 5>(a, sc, phases, s);
         default: return cudaErrorInvalidValue;
     }
 }
 
-template cudaError_t launch_eval_binned<double>(const EvalArgs<double>&, const BinnedScratch&, cudaStream_t);
-template cudaError_t launch_eval_binned<float>(const EvalArgs<float>&, const BinnedScratch&, cudaStream_t);
+template cudaError_t launch_eval_binned<double>(const EvalArgs<double>&, const BinnedScratch&, cudaStream_t, int);
+template cudaError_t launch_eval_binned<float>(const EvalArgs<float>&, const BinnedScratch&, cudaStream_t, int);
 template int binned_tile_count<double>(const EvalArgs<double>&);
 template int binned_tile_count<float>(const EvalArgs<float>&);
 

@@ -46,8 +46,11 @@ size_t binned_scratch_bytes(long long q, int max_tiles, size_t* offsets /*[8]*/)
 BinnedScratch binned_scratch_view(void* base, long long q, int max_tiles);
 template <typename R>
 int binned_tile_count(const EvalArgs<R>& a);  // 0 when the binned path does not apply
+// phases: sort the queries into `sc` (needs a.pts), evaluate the sorted batch (needs a.out), or both
+enum { kBinnedSort = 1, kBinnedEval = 2 };
 template <typename R>
-cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s);
+cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s,
+                               int phases = kBinnedSort | kBinnedEval);
 
 // span - order per axis, int32 [q][dim]
 template <typename R>

@@ -210,6 +210,11 @@ class InterpolationFunction:
         check(lib().bspl_evaluate_fields(self._h, pp, q, op, dev, sp))
         return out.reshape(self.n_fields, q) if not _is_device(out) else out.view(self.n_fields, q)
 
+    def eval_proxy(self, points, stream=None):
+        """Locate (and, for large 3-D batches, tile-sort) the query points once; the returned
+        plan evaluates any function of the same template at them (InterpolationTemplate.hpp:145-176)."""
+        return QueryPlan(self, points, stream)
+
     def locate(self, points):
         """span - order per axis (first control point index), int32 [q][dim]."""
         pts = np.ascontiguousarray(points, dtype=self.dtype).reshape(-1, self.dim)
@@ -217,6 +222,57 @@ class InterpolationFunction:
         check(lib().bspl_locate(self._h, pts.ctypes.data_as(C.c_void_p), pts.shape[0],
                                 cell.ctypes.data_as(C.POINTER(C.c_int32)), 0, None))
         return cell
+
+
+class QueryPlan:
+    """Device analogue of the reference's eval_proxy closure: query-dependent work done once."""
+
+    def __init__(self, fn, points, stream=None):
+        self._h = None
+        self.dim, self.dtype = fn.dim, fn.dtype
+        if _is_device(points):
+            import torch
+            pts = points.contiguous()
+            self.q = pts.numel() // fn.dim
+            sp = stream if stream is not None else torch.cuda.current_stream(pts.device).cuda_stream
+            ptr, dev, sp = C.c_void_p(pts.data_ptr()), 1, C.c_void_p(sp)
+        else:
+            pts = np.ascontiguousarray(points, dtype=fn.dtype).reshape(-1, fn.dim)
+            self.q = pts.shape[0]
+            ptr, dev, sp = pts.ctypes.data_as(C.c_void_p), 0, None
+        out = C.c_void_p()
+        check(lib().bspl_query_plan_create(fn._h, ptr, self.q, dev, sp, C.byref(out)))
+        self._h = out
+
+    def __call__(self, fn, field=0, derivatives=None, value_grad=False, out=None, device_out=False, stream=None):
+        """Evaluate `fn` (same template) at the planned points; results in the original order."""
+        n_out = fn.dim + 1 if value_grad else 1
+        shape = (self.q, n_out) if value_grad else (self.q,)
+        dv = None
+        if derivatives is not None:
+            _keep, dv = _i32(derivatives)
+        if device_out or _is_device(out):
+            import torch
+            if out is None:
+                out = torch.empty(shape, dtype=torch.float64 if self.dtype == np.float64 else torch.float32,
+                                  device="cuda")
+            sp = stream if stream is not None else torch.cuda.current_stream(out.device).cuda_stream
+            check(lib().bspl_query_plan_evaluate(self._h, fn._h, field, dv, int(value_grad),
+                                                 C.c_void_p(out.data_ptr()), 1, C.c_void_p(sp)))
+            return out
+        if out is None:
+            out = np.empty(shape, dtype=self.dtype)
+        check(lib().bspl_query_plan_evaluate(self._h, fn._h, field, dv, int(value_grad),
+                                             out.ctypes.data_as(C.c_void_p), 0, None))
+        return out
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().bspl_query_plan_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
 
 
 class InterpolationFunctionTemplate:

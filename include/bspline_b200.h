@@ -160,6 +160,22 @@ int bspl_evaluate_value_grad(const bspl_function* fn, int64_t field, const void*
  * operator() where the two disagree): out [n_fields][q]. */
 int bspl_evaluate_fields(const bspl_function* fn, const void* pts, int64_t q, void* out,
                          int on_device, void* stream);
+/* eval_proxy (InterpolationTemplate.hpp:145-176, Interpolation.hpp:493-506): the work that
+ * depends only on the query points -- locating them and, on the binned path, sorting them by
+ * coefficient tile -- done once and reused for any number of evaluations (any field, any
+ * derivative, any function built from the same template).  The plan keeps its own device copy
+ * of what it needs; `pts` may be released after the call returns (host) / after the stream
+ * reaches this point (device). */
+typedef struct bspl_query_plan bspl_query_plan;
+int bspl_query_plan_create(const bspl_function* fn, const void* pts, int64_t q, int on_device,
+                           void* stream, bspl_query_plan** out);
+/* value_grad == 0: out[q] (deriv == NULL: values); != 0: out[q][1+dim].  Results are in the
+ * order of the original points. */
+int bspl_query_plan_evaluate(const bspl_query_plan* plan, const bspl_function* fn, int64_t field,
+                             const int* deriv, int value_grad, void* out, int on_device,
+                             void* stream);
+void bspl_query_plan_destroy(bspl_query_plan* plan);
+
 /* get_knot_iter (BSpline.hpp:125-157): cell[q][dim] = span - order per axis,
  * exactly the first control-point index the reference selects. */
 int bspl_locate(const bspl_function* fn, const void* pts, int64_t q, int32_t* cell,

@@ -72,6 +72,20 @@ if __name__ == "__main__":
         eval_case((64, 64, 64), 3, 1 << 24)
         eval_case((1024, 1024), 3, 1 << 24)
         eval_case((1 << 24,), 5, 1 << 24, per=[True])
+    if which == "plan":
+        shape = (256, 256, 256)
+        t = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 3)
+        fn = t.interpolate(field(shape))
+        for lq in (24, 26, 28):
+            Q = 1 << lq
+            pts = torch.rand((Q, 3), dtype=torch.float64, device="cuda")
+            out = torch.empty((Q, 4), dtype=torch.float64, device="cuda")
+            plan = fn.eval_proxy(pts)
+            ms = timeit(lambda: plan(fn, value_grad=True, out=out))[1]
+            ms0 = timeit(lambda: fn.value_grad(pts, out=out))[1]
+            print("Q=2^%d: planned value+grad %.3f ms (%.2f Gpts/s); one-shot %.3f ms (%.2f Gpts/s)" % (
+                lq, ms, Q / ms / 1e6, ms0, Q / ms0 / 1e6), flush=True)
+            del plan, pts, out
     if which == "fields":
         F, shape, Q = 4096, (128, 128), 1 << 20
         t = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 2)

@@ -495,3 +495,34 @@ def test_non_finite_queries_do_not_disturb_the_batch(pkg):
                 pkg.set_eval_path("auto")
             assert np.array_equal(got[good], ref[good])
             assert np.isnan(got[rows[:200], 0]).all()
+
+
+@pytest.mark.parametrize("path", ["direct", "binned"])
+def test_eval_proxy_query_plan(pkg, path):
+    """eval_proxy analogue: one plan (locate + tile sort), many evaluations -- other fields, other
+    functions of the same template, derivatives, value+gradient, host and device outputs."""
+    import torch
+    rng = np.random.default_rng(23)
+    shape = (36, 41, 30)
+    per = [True, False, False]
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 2.0), (0.0, 1.0), (-1.0, 1.0)], per)
+    f1 = np.stack([smooth_field(shape, rng) for _ in range(2)])
+    fa = t.interpolate(f1)
+    fb = t.interpolate(smooth_field(shape, rng))
+    pts = np.array([0.0, 0.0, -1.0]) + rng.uniform(0, 1, (40000, 3)) * np.array([2.0, 1.0, 2.0])
+    try:
+        pkg.set_eval_path(path)
+        plan = fa.eval_proxy(torch.from_numpy(pts).cuda())
+        plan_h = fb.eval_proxy(pts)  # built from host points
+        assert np.array_equal(plan(fa, field=1), fa.evaluate(pts, field=1))
+        assert np.array_equal(plan(fb), fb.evaluate(pts))
+        assert np.array_equal(plan_h(fa, value_grad=True), fa.value_grad(pts))
+        assert np.array_equal(plan(fb, derivatives=[1, 0, 2]), fb.derivative(pts, [1, 0, 2]))
+        assert not plan(fb, derivatives=[4, 0, 0]).any()
+        dev = plan(fb, value_grad=True, device_out=True)
+        assert np.array_equal(dev.cpu().numpy(), fb.value_grad(pts))
+        other = pkg.InterpolationFunction(3, smooth_field(shape, rng), [(0.0, 2.0), (0.0, 1.0), (-1.0, 1.0)], per)
+        with pytest.raises(pkg.BsplError):
+            plan(other)  # a different template
+    finally:
+        pkg.set_eval_path("auto")
