@@ -147,6 +147,7 @@ template <typename T> constexpr bspl_dtype dtype_of() {
 }
 
 struct FnDeleter { void operator()(bspl_function* p) const { bspl_function_destroy(p); } };
+struct PlanDeleter { void operator()(bspl_query_plan* p) const { bspl_query_plan_destroy(p); } };
 struct TmDeleter { void operator()(bspl_template* p) const { bspl_template_destroy(p); } };
 using FnHandle = std::unique_ptr<bspl_function, FnDeleter>;
 using TmHandle = std::unique_ptr<bspl_template, TmDeleter>;
@@ -184,6 +185,39 @@ inline void set_device(int ordinal) { b200_detail::default_device() = ordinal; }
 
 template <typename T, std::size_t D, std::size_t O, typename U>
 class InterpolationFunctionTemplate;
+template <typename T, std::size_t D, std::size_t O, typename U>
+class InterpolationFunction;
+
+// What eval_proxy returns (Interpolation.hpp:493-506, InterpolationTemplate.hpp:145-176): the
+// query-dependent work done once, applicable to any function of the same template.  Copyable.
+template <typename T, std::size_t D, std::size_t O, typename U>
+class EvalProxy {
+   public:
+    using function_type = InterpolationFunction<T, D, O, U>;
+    EvalProxy(const bspl_function* fn, const U* points, std::size_t q) : q_(q) {
+        bspl_query_plan* p = nullptr;
+        b200_detail::check(bspl_query_plan_create(fn, points, static_cast<int64_t>(q), 0, nullptr, &p));
+        plan_.reset(p, b200_detail::PlanDeleter());
+    }
+    // single point, like the reference's closure: proxy(interp) -> value
+    T operator()(const function_type& interp) const {
+        T v{};
+        b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, &v, 0, nullptr));
+        return v;
+    }
+    // batched: out[q]
+    void operator()(const function_type& interp, T* out) const {
+        b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, out, 0, nullptr));
+    }
+    void value_grad(const function_type& interp, T* out) const {
+        b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 1, out, 0, nullptr));
+    }
+    std::size_t size() const { return q_; }
+
+   private:
+    std::shared_ptr<bspl_query_plan> plan_;
+    std::size_t q_;
+};
 
 // ---------------------------------------------------------------- InterpolationFunction
 template <typename T, std::size_t D, std::size_t O, typename U = double>
@@ -315,6 +349,14 @@ class InterpolationFunction {
     void evaluate_value_grad_device(const coord_type* d_points, size_type q, val_type* d_out,
                                     void* stream = nullptr) const {
         b200_detail::check(bspl_evaluate_value_grad(need(), 0, d_points, static_cast<int64_t>(q), d_out, 1, stream));
+    }
+
+    // eval_proxy (Interpolation.hpp:493-506): one point, or a batch of q points [q][D]
+    EvalProxy<T, D, O, U> eval_proxy(DimArray<coord_type> coord) const {
+        return EvalProxy<T, D, O, U>(need(), coord.data(), 1);
+    }
+    EvalProxy<T, D, O, U> eval_proxy(const coord_type* points, size_type q) const {
+        return EvalProxy<T, D, O, U>(need(), points, q);
     }
 
     // ---- properties (Interpolation.hpp:248-267)

@@ -107,6 +107,21 @@ int main() {
     expect(worst < 1e-13, "fused value+gradient == separate calls", worst);
     auto copy = interp3;  // value semantics
     expect(copy(coords_3d[0], coords_3d[1], coords_3d[2]) == interp3(coords_3d[0], coords_3d[1], coords_3d[2]), "copy");
+    {   // eval_proxy: weights/location once, applied to two functions of the same template
+        Mesh<double, 3> g3d{5, 6, 7};
+        for (std::size_t i = 0; i < 210; ++i) g3d(g3d.dimension().dimwise_indices(i)) = 2. * f3[i] - 1.;
+        auto other = tmpl.interpolate(g3d);
+        std::array<double, 3> c{coords_3d[0], coords_3d[1], coords_3d[2]};
+        auto proxy = interp3.eval_proxy(c);
+        expect(proxy(interp3) == interp3(c) && proxy(other) == other(c), "eval_proxy (single point, two functions)");
+        auto batch_proxy = interp3.eval_proxy(coords_3d.data(), vals_3d.size());
+        std::vector<double> pv(vals_3d.size());
+        batch_proxy(other, pv.data());
+        bool same = true;
+        for (std::size_t i = 0; i < pv.size(); ++i)
+            same = same && pv[i] == other(coords_3d[3 * i], coords_3d[3 * i + 1], coords_3d[3 * i + 2]);
+        expect(same, "eval_proxy (batched)");
+    }
     InterpolationFunction<double, 3, 3> into;
     tmpl.interpolate(into, f3d);
     expect(into(1., 2., 3.) == interp3(1., 2., 3.), "interpolate(function&, mesh)");
