@@ -7,8 +7,7 @@
 // read once per tile, plus a sorted copy of the queries (coordinates + original index).
 //
 // Pipeline, all on the caller's stream, no host synchronisation:
-//   1. key_count    : locate each query, key = (tile, x, y cell in tile) -> key_of[q],
-//                     histogram over keys
+//   1. key_count    : locate each query, key = (tile, x, y cell in tile), histogram over keys
 //   2. plan         : exclusive scan of the histogram, cursors, per-tile work list
 //                     (tile, begin, end) in chunks of kChunk queries
 //   3. scatter      : rec[cursor[key]++] = {x, y, z, q}  (counting sort, tile-major)
@@ -55,24 +54,17 @@ __device__ __forceinline__ uint32_t key_of_point(const BinParams<R>& p, long lon
     constexpr int T = tile_edge<O>();
     int c[3];
 #pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        R x = p.pts[q * 3 + d];
-        c[d] = locate<R, O>(p.ax[d], x) - O;
-    }
+    for (int d = 0; d < 3; ++d) c[d] = locate_quick<R, O>(p.ax[d], p.pts[q * 3 + d]) - O;
     const int tx = c[0] / T, ty = c[1] / T, tz = c[2] / T;
     const int tile = (tx * p.ntile[1] + ty) * p.ntile[2] + tz;
     return static_cast<uint32_t>(tile) * (T * T) + (c[0] - tx * T) * T + (c[1] - ty * T);
 }
 
 template <typename R, int O>
-__global__ void __launch_bounds__(512) key_count_kernel(const BinParams<R> p, uint32_t* __restrict__ key_of,
-                                                        uint32_t* __restrict__ counts) {
+__global__ void __launch_bounds__(512) key_count_kernel(const BinParams<R> p, uint32_t* __restrict__ counts) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < p.q; q += stride) {
-        const uint32_t k = key_of_point<R, O>(p, q);
-        key_of[q] = k;
-        atomicAdd(&counts[k], 1u);
-    }
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < p.q; q += stride)
+        atomicAdd(&counts[key_of_point<R, O>(p, q)], 1u);
 }
 
 // Per-tile totals of the key histogram: one warp per tile.
@@ -161,16 +153,18 @@ template <typename R> struct Rec;
 template <> struct __align__(32) Rec<double> { double x, y, z; unsigned long long idx; };
 template <> struct __align__(16) Rec<float> { float x, y, z; uint32_t idx; };
 
-template <typename R>
-__global__ void __launch_bounds__(512) scatter_kernel(const uint32_t* __restrict__ key_of, const R* __restrict__ pts,
-                                                      long long q, uint32_t* __restrict__ cursor,
+// The key is recomputed here rather than stored by the counting pass: this kernel waits on
+// random sector writes (issue slots ~2 % busy), so the arithmetic is free and 8 bytes of traffic
+// per query disappear.
+template <typename R, int O>
+__global__ void __launch_bounds__(512) scatter_kernel(const BinParams<R> p, uint32_t* __restrict__ cursor,
                                                       Rec<R>* __restrict__ rec) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < q; i += stride) {
+    for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.q; i += stride) {
         Rec<R> r;
-        r.x = pts[3 * i]; r.y = pts[3 * i + 1]; r.z = pts[3 * i + 2];
+        r.x = p.pts[3 * i]; r.y = p.pts[3 * i + 1]; r.z = p.pts[3 * i + 2];
         r.idx = static_cast<decltype(r.idx)>(i);
-        const uint32_t pos = atomicAdd(&cursor[key_of[i]], 1u);
+        const uint32_t pos = atomicAdd(&cursor[key_of_point<R, O>(p, i)], 1u);
         rec[pos] = r;
     }
 }
@@ -446,12 +440,12 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, int pha
         e = cudaMemsetAsync(sc.counts, 0, sizeof(uint32_t) * n_bins, s);
         if (e != cudaSuccess) return e;
         const int grid = kSMs * 4;
-        key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.tile_of, sc.counts);
+        key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.counts);
         const int tgrid = (n_tiles * 32 + 255) / 256;
         tile_totals_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_total);
         plan_kernel<<<1, 1024, 0, s>>>(sc.tile_total, n_tiles, sc.tile_off, sc.work, sc.n_work, sc.next_item);
         key_cursor_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_off, sc.cursor);
-        scatter_kernel<R><<<grid, 512, 0, s>>>(sc.tile_of, a.pts, a.q, sc.cursor, static_cast<Rec<R>*>(sc.rec));
+        scatter_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.cursor, static_cast<Rec<R>*>(sc.rec));
         count_launch(5);
         e = cudaGetLastError();
         if (e != cudaSuccess || !(phases & kBinnedEval)) return e;
@@ -485,7 +479,7 @@ size_t binned_scratch_bytes(long long q, int max_tiles, size_t* offsets) {
     // layout: key_of[q] | rec[q] (32 bytes each) | counts | cursor | work[3*(q/kChunk + max_tiles)] | n_work, next | ...
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
-    offsets[0] = take(sizeof(uint32_t) * q);
+    offsets[0] = take(256);  // (formerly the per-query key array)
     offsets[1] = take(32 * static_cast<size_t>(q));
     offsets[2] = take(sizeof(uint32_t) * max_tiles * 256);  // one counter per (tile, x, y) key
     offsets[3] = take(sizeof(uint32_t) * max_tiles * 256);

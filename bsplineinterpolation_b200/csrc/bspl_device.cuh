@@ -92,6 +92,39 @@ __device__ __forceinline__ int locate(const AxisParams<R>& a, R& x) {
     return lo - 1;
 }
 
+// locate() with a short cut for uniform axes: when the guessed span and its neighbours lie among
+// the formula knots (away from the clamped ends) the answer is decided by at most four knot
+// values computed without the clamp logic; anything else falls back to locate().  Same knots,
+// same comparisons, hence the same span.  x is NOT updated (periodic wrap stays local).
+template <typename R, int O>
+__device__ __forceinline__ int locate_quick(const AxisParams<R>& a, R x) {
+    using A = Arith<R>;
+    if (a.t == nullptr) {
+        R xw = x;
+        if (a.periodic) {
+            const R period = A::sub(a.second, a.first);
+            xw = A::add(A::add(a.first, A::fmodr(A::sub(x, a.first), period)), x < a.first ? period : R(0));
+        }
+        const R g = A::floorr((xw - a.lo) * a.inv_dx + a.half_extra);
+        const R g_lo = static_cast<R>(a.periodic ? O + 1 : O + 2), g_hi = static_cast<R>(a.K - O - 4);
+        if (g >= g_lo && g <= g_hi) {  // knots g-1 .. g+2 are formula knots and g-1 .. g+1 valid spans
+            const R t0 = A::add(a.lo, A::mul(A::sub(g, a.half_extra), a.dx));
+            const R t1 = A::add(a.lo, A::mul(A::sub(g + R(1), a.half_extra), a.dx));
+            const int s = static_cast<int>(g);
+            if (t0 <= xw) {
+                if (xw < t1) return s;
+                const R t2 = A::add(a.lo, A::mul(A::sub(g + R(2), a.half_extra), a.dx));
+                if (xw < t2) return s + 1;
+            } else {
+                const R tm = A::add(a.lo, A::mul(A::sub(g - R(1), a.half_extra), a.dx));
+                if (tm <= xw) return s - 1;
+            }
+        }
+    }
+    R xx = x;
+    return locate<R, O>(a, xx);
+}
+
 // Local knot window tk[m] = t[span - O + 1 + m], m = 0 .. 2O-1.
 template <typename R, int O>
 __device__ __forceinline__ void load_knot_window(const AxisParams<R>& a, int span, R* tk) {
