@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kEvalThreads, 2)
         if (tid == 0) s_item = atomicAdd(p.next_item, 1u);
         __syncthreads();  // publishes s_item; every thread is past its reads of the previous brick
         const uint32_t item = s_item;
+        __syncthreads();  // s_item is rewritten by thread 0 at the top of the next iteration
         if (item >= n_work) break;
         const uint32_t tile = p.work[3 * item], begin = p.work[3 * item + 1], end = p.work[3 * item + 2];
         const int tz = tile % p.ntile[2], ty = (tile / p.ntile[2]) % p.ntile[1], tx = tile / (p.ntile[2] * p.ntile[1]);
