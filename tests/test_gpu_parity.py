@@ -415,7 +415,7 @@ def test_baseline_cfg3_3d_cubic_256_sample(pkg):
     _same_control_points(fn.control_points(), o.control_points())
     pts = rng.uniform(0, 1, (1 << 22, 3))
     d = torch.from_numpy(pts).cuda()
-    vg = fn.value_grad(d).cpu().numpy()           # auto -> binned (Q >= 256 * tiles)
+    vg = fn.value_grad(d).cpu().numpy()           # auto -> binned (Q >= 2^20 and >= 40 * tiles)
     try:
         pkg.set_eval_path("direct")
         vd = fn.value_grad(d).cpu().numpy()
