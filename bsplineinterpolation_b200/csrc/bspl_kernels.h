@@ -52,6 +52,13 @@ template <typename R>
 cudaError_t launch_eval_binned(const EvalArgs<R>& a, const BinnedScratch& sc, cudaStream_t s,
                                int phases = kBinnedSort | kBinnedEval);
 
+// Many fields of one small 2-D mesh at one query set: fields streamed through shared memory
+// with bulk asynchronous copies, weights kept in registers (bspl_fields.cu).
+template <typename R>
+bool fields_smem_eligible(const EvalArgs<R>& a);
+template <typename R>
+cudaError_t launch_eval_fields_smem(const EvalArgs<R>& a, cudaStream_t s);
+
 // span - order per axis, int32 [q][dim]
 template <typename R>
 cudaError_t launch_locate(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s);

@@ -526,3 +526,25 @@ def test_eval_proxy_query_plan(pkg, path):
             plan(other)  # a different template
     finally:
         pkg.set_eval_path("auto")
+
+
+@pytest.mark.parametrize("order,periodic", [(3, (True, False)), (2, (False, True)), (5, (False, False)), (1, (True, True))])
+def test_many_fields_streamed_through_shared_memory(pkg, order, periodic):
+    """evaluate_fields on a small 2-D mesh takes the field-streaming kernel (weights once per query,
+    fields through shared memory): must equal per-field evaluation and the oracle."""
+    import torch
+    rng = np.random.default_rng(60 + order)
+    F, shape, Q = 12, (48, 56), 9000
+    fields = rng.standard_normal((F,) + shape)
+    t = pkg.InterpolationFunctionTemplate(order, shape, [(0.0, 1.0), (-1.0, 2.0)], periodic)
+    fn = t.interpolate(fields)
+    pts = np.array([0.0, -1.0]) + rng.uniform(-0.1, 1.1, (Q, 2)) * np.array([1.0, 3.0])
+    allv = fn.evaluate_fields(torch.from_numpy(pts).cuda()).cpu().numpy()
+    host = fn.evaluate_fields(pts)
+    assert np.array_equal(allv, host)
+    for k in (0, 5, F - 1):
+        single = fn.evaluate(pts, field=k)
+        assert np.abs(allv[k] - single).max() <= 1e-13 * np.abs(single).max()
+        o = OracleSpline(order, shape, periodic, lo=[0, -1], hi=[1, 2], f=fields[k])
+        inside = np.all((pts >= [0, -1]) & (pts <= [1, 2]), axis=1) | np.array(periodic).all()
+        _close(allv[k][inside], o.eval(pts[inside]))
