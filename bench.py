@@ -86,6 +86,21 @@ class CpuReference:
                 % (CPU_SAMPLE, self.threads, dt, self.construct_s))
 
 
+def cpu_reference_solve():
+    """The reference's own InterpolationFunctionTemplate::interpolate on the 512^3 mesh, with its
+    INTP_MULTITHREAD pool (hard-wired to 8 workers + the caller, InterpolationTemplate.hpp:554) and
+    without the cell-layout fill; template construction is not timed."""
+    from oracle import pyoracle
+    pyoracle.build()
+    lib = os.path.join(pyoracle.OUT, "libintp_ref_plain_mt.so")
+    if not os.path.exists(lib):
+        return None
+    f = smooth_field_np(SOLVE_MESH)
+    sp = pyoracle.RefSpline(ORDER, f, [0, 0, 0], lo=[0, 0, 0], hi=[1, 1, 1], kind="plain_mt")
+    return {"ms": sp.interpolate_ms, "kind": "reference", "threads": "reference pool: 8 workers + caller",
+            "host_cores": os.cpu_count(), "config": "INTP_MULTITHREAD, plain layout (no INTP_CELL_LAYOUT)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -300,6 +315,10 @@ def run_gpu(args):
         sbytes = 2 * 8 * 3 * float(np.prod(SOLVE_MESH))
         solve = {"mesh": list(SOLVE_MESH), "ms": ms, "target_ms": 50.0,
                  "algorithmic_gbs": sbytes / ms / 1e6, "roofline_frac": sbytes / ms / 1e6 / hbm_peak}
+        del sf, sfn, st
+        torch.cuda.empty_cache()
+        if rank == 0 and world == 1 and not args.no_cpu:
+            solve["cpu_reference"] = cpu_reference_solve()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

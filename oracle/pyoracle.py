@@ -28,7 +28,7 @@ def build(ref="/root/reference", force=False):
     """Compile the C port and, if the reference checkout exists, the ref shim."""
     need = force or not os.path.exists(os.path.join(OUT, "libbspl_oracle.so"))
     if os.path.isdir(os.path.join(ref, "src/include")):
-        for n in ("libintp_ref_cell.so", "libintp_ref_plain.so"):
+        for n in ("libintp_ref_cell.so", "libintp_ref_plain.so", "libintp_ref_plain_mt.so"):
             need = need or not os.path.exists(os.path.join(OUT, n))
     if need:
         args = ["make", "-f", os.path.join(HERE, "Makefile"), "all", "REF=" + ref]
@@ -208,7 +208,8 @@ def ref_available():
 
 
 def ref_lib(kind):
-    """kind: 'cell' (INTP_CELL_LAYOUT + INTP_MULTITHREAD) or 'plain'."""
+    """kind: 'cell' (INTP_CELL_LAYOUT + INTP_MULTITHREAD), 'plain', or 'plain_mt' (plain layout +
+    INTP_MULTITHREAD: the reference's threaded solve without the cell-layout fill)."""
     if kind not in _ref:
         L = C.CDLL(os.path.join(OUT, "libintp_ref_%s.so" % kind))
         L.intp_ref_create.restype = C.c_void_p
@@ -266,7 +267,7 @@ class RefSpline:
         return (out[0], out[1])
 
     def control_points(self):
-        assert self.kind == "plain", "plain control points need the non-cell-layout build"
+        assert self.kind in ("plain", "plain_mt"), "plain control points need a non-cell-layout build"
         out = np.empty(self.L.intp_ref_ctrl_size(self.h))
         self.L.intp_ref_ctrl(self.h, _ptr(out))
         return out.reshape(self.shape)

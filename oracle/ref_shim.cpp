@@ -5,14 +5,16 @@
 // intp::InterpolationFunction<double, D, O> for D in 1..3, O in 0..5 and
 // exposes what the parity tests and the CPU-baseline timing need: knots,
 // ranges, spans, plain control points, values, mixed derivatives and a timed
-// InterpolationFunctionTemplate::interpolate.  Two shared objects are built
+// InterpolationFunctionTemplate::interpolate.  Three shared objects are built
 // from this one file (see oracle/Makefile):
 //   _ref/libintp_ref_cell.so   -DINTP_CELL_LAYOUT -DINTP_MULTITHREAD  (the
 //                              reference's own Release test configuration,
 //                              test/CMakeLists.txt:43-47) -> eval + timing
 //   _ref/libintp_ref_plain.so  no INTP_CELL_LAYOUT -> spline().control_points()
 //                              is the plain N-d array (BSpline.hpp:58-61)
-// Both define INTP_PERIODIC_NO_DUMMY_POINT like the reference test build.
+//   _ref/libintp_ref_plain_mt.so  plain layout + INTP_MULTITHREAD -> the threaded
+//                              solve baseline without the 16x cell-layout fill
+// All define INTP_PERIODIC_NO_DUMMY_POINT like the reference test build.
 #include <Interpolation.hpp>
 
 #include <chrono>
@@ -107,13 +109,8 @@ struct Ref final : RefBase {
             if (ax[d].coords) mask |= size_t{1} << d;
         }
         intp::Mesh<double, D> mesh{intp::MeshDimension<D>(dims)};
-        {
-            // Mesh exposes only const data(); fill through linear indices.
-            size_t total = mesh.size();
-            for (size_t i = 0; i < total; ++i) {
-                mesh(mesh.dimension().dimwise_indices(i)) = f[i];
-            }
-        }
+        // Mesh exposes only a const data(); the storage is row-major like f (Mesh.hpp:241-246)
+        std::copy(f, f + mesh.size(), const_cast<double*>(mesh.data()));
         bool ok = try_build<0>(mask, *this, per, mesh, ax, repeat);
         if constexpr (D == 1) {
             ok = ok || try_build<1>(mask, *this, per, mesh, ax, repeat);
