@@ -159,6 +159,31 @@ def test_committed_reference_outputs(pkg):
         _close(fn.derivative(pts, [int(v) for v in data["c%d_dv" % c]]), data["c%d_dvals" % c], 1e-9)
 
 
+def test_committed_reference_outputs_fp32(pkg):
+    """The reference instantiated with T = U = float (tests/golden/ref_outputs_f32.npz, made by
+    make_ref_outputs_f32.py): spans bit-exact, values / derivatives / control points within the north star's
+    fp32 tolerance of 1e-5 (relative to the largest magnitude)."""
+    import os
+    from conftest import ROOT
+    data = np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs_f32.npz"))
+    tol = 1e-5
+    for c in range(int(data["n_cases"])):
+        order = int(data["c%d_order" % c]); per = [bool(v) for v in data["c%d_periodic" % c]]
+        f = data["c%d_f" % c]
+        fn = pkg.InterpolationFunction(order, f, _ranges(data["c%d_lo" % c], data["c%d_hi" % c]), per, dtype=np.float32)
+        assert fn.dtype == np.float32
+        ctrl = data["c%d_ctrl" % c]
+        assert np.abs(fn.control_points() - ctrl).max() <= tol * np.abs(ctrl).max()
+        pts = data["c%d_pts" % c]
+        assert pts.dtype == np.float32
+        assert np.array_equal(fn.locate(pts), data["c%d_spans" % c])
+        vals = data["c%d_vals" % c]
+        assert np.abs(fn(pts) - vals).max() <= tol * np.abs(vals).max()
+        dvals = data["c%d_dvals" % c]
+        got = fn.derivative(pts, [int(v) for v in data["c%d_d1" % c]])
+        assert np.abs(got - dvals).max() <= tol * np.abs(dvals).max()
+
+
 def test_band_solver(pkg):
     """band-matrix-and-solver-test.cpp: ||b - A x|| / ||b|| < 1e-10, and bit parity with the oracle."""
     from test_oracle import _band_matrices
