@@ -166,6 +166,16 @@ struct BandFactor {
     ZeroBuf<R> right;       // [n][p]:     A(i, n-p+c)  (rows above the band)
     ZeroBuf<R> bottom;      // [q][n]:     A(n-q+r, j)  (columns left of the band)
     int64_t right_rows = 0;   // rows >= right_rows of the right strip were never written
+    // Compact form (build_axis_factor): the matrix really has true_n rows; stored row r is true
+    // row r for r < head, true row r + (true_n - n) for the last n - head rows, and every true
+    // row in between equals stored row head - 1.  true_n == 0: stored as is.
+    int64_t true_n = 0, head = 0;
+    int64_t full_n() const { return true_n ? true_n : n; }
+    int64_t stored_row(int64_t i) const {
+        if (!true_n || i < head) return i;
+        const int64_t tail0 = true_n - (n - head);
+        return i >= tail0 ? i - (true_n - n) : head - 1;
+    }
     int64_t bottom_cols = 0;  // columns >= bottom_cols of the bottom strip were never written
 
     void init(int64_t n_, int p_, int q_, bool cyclic_) {
@@ -283,20 +293,31 @@ struct BandFactor {
 
 // Collocation matrix of one axis, factored (build_solver_,
 // InterpolationTemplate.hpp:254-446).
+//
+// Long uniform axes are factored in COMPACT form: away from its two ends the matrix is
+// translation invariant (every interior row is the same basis evaluation, :341-360 / :273-280),
+// so the elimination settles into a state that repeats bit for bit and the corner strips of a
+// periodic axis underflow to exact zeros.  Rows [0, head) and the last n_stored - head rows are
+// then factored on a surrogate of n_stored rows assembled from the TRUE axis (true abscissae and
+// knots at both ends); every row in between equals row head-1.  The surrogate is accepted only
+// if a 128-row window around the cut is bit-identical and the strips died out before it --
+// otherwise the full matrix is factored.  tests/test_abi.py compares the expansion with the
+// full-size factorisation bit for bit.
+constexpr int64_t kCompactRows = 4096;      // surrogate size
+constexpr int64_t kCompactMinAxis = 16384;  // axes shorter than this are factored in full
+
 template <typename R>
-void build_axis_factor(const HostAxis<R>& a, BandFactor<R>& m) {
+void assemble_axis_rows(const HostAxis<R>& a, BandFactor<R>& m, int64_t stored, int64_t head, int bw) {
     const int O = a.order;
-    const int64_t N = a.n, K = a.K;
-    const int bw = a.periodic ? O / 2 : (O == 0 ? 0 : O - 1);
-    if (N <= 2 * bw + 1 && a.periodic && bw > 0)
-        throw std::invalid_argument("periodic axis too short for this order");
-    m.init(N, bw, bw, a.periodic);
+    const int64_t N = a.n, K = a.K, shift = N - stored;
+    m.init(stored, bw, bw, a.periodic);
     R bsv[16] = {0};
     if (a.periodic && a.uniform)  // one evaluation serves every row (:273-280)
         a.basis(O, a.knot(O) + static_cast<R>(1 - O % 2) * a.dx * R(.5), bsv);
-    for (int64_t i = 0; i < N; ++i) {
+    for (int64_t r = 0; r < stored; ++r) {
+        const int64_t i = r < head ? r : r + shift;  // true data index of stored row r
         if (!a.periodic && (i == 0 || i == N - 1)) {  // end rows interpolate exactly (:317-329)
-            m.main(i, i) = 1;
+            m.main(r, r) = 1;
             continue;
         }
         int64_t seg;
@@ -318,18 +339,45 @@ void build_axis_factor(const HostAxis<R>& a, BandFactor<R>& m) {
             a.basis(seg, x, bsv);
         }
         const int cnt = a.periodic ? (O | 1) : O == 1 ? 1 : (a.uniform && internal) ? (O | 1) : O + 1;
-        const int64_t row0 = i + (a.periodic ? bw : 0), col0 = seg - O;
-        if (row0 < N && col0 + cnt <= N && col0 + bw >= row0 && row0 + bw >= col0 + cnt - 1) {
+        // placement in stored coordinates (identical to the true ones when nothing is cut out)
+        const int64_t row0 = r + (a.periodic ? bw : 0), col0 = seg - (i - r) - O;
+        if (row0 < stored && col0 + cnt <= stored && col0 + bw >= row0 && row0 + bw >= col0 + cnt - 1) {
             // no wrap, whole row inside the band: the common case on long axes
             for (int j = 0; j < cnt; ++j) m.main(row0, col0 + j) = bsv[j];
         } else {
             for (int j = 0; j < cnt; ++j) {
-                const int64_t row = row0 % N;
-                const int64_t col = (col0 + j) % N;
+                const int64_t row = row0 % stored;
+                const int64_t col = (col0 + j) % stored;
                 m.at(row, col) = bsv[j];
             }
         }
     }
+}
+
+template <typename R>
+void build_axis_factor(const HostAxis<R>& a, BandFactor<R>& m, bool allow_compact = true) {
+    const int O = a.order;
+    const int64_t N = a.n;
+    const int bw = a.periodic ? O / 2 : (O == 0 ? 0 : O - 1);
+    if (N <= 2 * bw + 1 && a.periodic && bw > 0)
+        throw std::invalid_argument("periodic axis too short for this order");
+    if (allow_compact && a.uniform && N >= kCompactMinAxis) {
+        const int64_t head = kCompactRows / 2, guard = 64;
+        assemble_axis_rows(a, m, kCompactRows, head, bw);
+        m.factor();
+        const int w = m.p + m.q + 1;
+        bool steady = !m.cyclic || (m.right_rows <= head - guard && m.bottom_cols <= head - guard);
+        for (int64_t r = head - guard + 1; r < head + guard && steady; ++r)
+            for (int c = 0; c < w && steady; ++c) steady = m.band[r * w + c] == m.band[(r - 1) * w + c];
+        if (steady) {
+            m.true_n = N;
+            m.head = head;
+            return;
+        }
+    }
+    assemble_axis_rows(a, m, N, N, bw);
+    m.true_n = 0;
+    m.head = 0;
     m.factor();
 }
 

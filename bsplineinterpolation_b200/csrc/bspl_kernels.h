@@ -77,6 +77,13 @@ struct AxisLU {
     int bottom_len;   // entries j >= bottom_len are exactly zero
     int right_len;    // entries i >= right_len are exactly zero (rows above the main band only)
     int bottom_sig;   // entries j >= bottom_sig are below 1e-30 of the largest (chunked sweeps only)
+    // Compact storage of long uniform axes (bspl_host.h: build_axis_factor): L, U and diag hold
+    // rows [0, head) and the last rows of the matrix; the `skip` rows cut out in between all
+    // equal row head-1.  Stored in full: head == n, skip == 0.
+    int head, skip;
+    __host__ __device__ __forceinline__ long long row(int j) const {
+        return j < head ? j : (j >= head + skip ? j - skip : head - 1);
+    }
 };
 
 // Geometry of one sweep over a (field, axis0, axis1, axis2) array: lines run

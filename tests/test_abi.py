@@ -94,10 +94,11 @@ def _row_form_from_oracle(o, n, P, per):
 @pytest.mark.parametrize("per", [0, 1])
 def test_host_template_construction_matches_oracle(lib_built, order, per):
     """Knots, ranges and LU factors bit-identical to the oracle's -- including long uniform axes,
-    where the host factorisation fast-forwards through its steady state."""
+    where the host factorisation fast-forwards through its steady state (n = 1500, 4099) or keeps only
+    both ends of the matrix (compact form, n = 20011)."""
     L = lib_built.lib()
     rng = np.random.default_rng(order * 2 + per)
-    for n in (7, 12, 33, 64, 1500, 4099):
+    for n in (7, 12, 33, 64, 1500, 4099, 20011):
         for nonuni in (0, 1):
             if nonuni and ((order == 0 and not per) or n > 64):
                 continue
