@@ -20,5 +20,14 @@ for order, per in ((3, [False, True, False]), (2, [True, False, False]), (5, [Fa
 B.InterpolationFunction(5, rng.standard_normal(60000), [(0.0, 1.0)], [True])
 B.InterpolationFunction(3, rng.standard_normal((300, 200)), [(0.0, 1.0)] * 2, [False, True])
 B.InterpolationFunction(3, rng.standard_normal((40, 50)), [(0.0, 1.0)] * 2, [True, False])
+# TMA-tiled contiguous sweep: fused with the mesh copy (ragged tiles: 70 lines per run, 72 columns),
+# with a shifted slow axis, in float, and in place after a rotating copy is not possible (odd strides fall back)
+B.InterpolationFunction(3, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, [False, False, False])
+B.InterpolationFunction(3, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, [True, False, False])
+B.InterpolationFunction(5, rng.standard_normal((66, 70, 72)).astype(np.float32), [(0.0, 1.0)] * 3, dtype=np.float32)
+B.InterpolationFunction(3, rng.standard_normal((66, 70, 73)), [(0.0, 1.0)] * 3, [False, False, False])
+tt = B.InterpolationFunctionTemplate(4, (80, 64, 96), [(0.0, 1.0)] * 3, [True, True, True])
+xx = torch.rand((80, 64, 96), dtype=torch.float64, device="cuda")
+tt.sweep_axis(2, xx, [1, 80, 64], [0, 64 * 96, 96], 1)
 torch.cuda.synchronize()
 print("sanitize case done")

@@ -315,6 +315,37 @@ def test_binned_tma_path_matches_direct_and_oracle(pkg, order, periodic):
     _close(g_b[inside, 2], o.deriv(pts[inside], [0, 1, 0]))
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_tma_tiled_contiguous_sweep_bit_exact(pkg, order):
+    """>= 4096 lines along the contiguous axis take the TMA-tiled sweep (bspl_solve.cu): fused with
+    the copy out of the caller's mesh when the last two axes carry no cyclic shift, in place
+    otherwise; ragged tiles (70 lines per run, 72 = 4.5 tile rows), a shifted slow axis, many
+    fields, host and device meshes, and an odd row length that TMA cannot address (falls back).
+    Control points bit-identical to the oracle's sequential solve in every case."""
+    import torch
+    rng = np.random.default_rng(4200 + order)
+    cases = [((66, 70, 72), [False, False, False]), ((66, 70, 72), [True, False, False]),
+             ((66, 70, 72), [False, True, True]), ((66, 70, 73), [False, False, False]),
+             ((260, 48), [False, False])]
+    for shape, per in cases:
+        dim = len(shape)
+        fields = 20 if dim == 2 else 1
+        f = rng.standard_normal((fields,) + shape)
+        t = pkg.InterpolationFunctionTemplate(order, shape, [(0.0, 1.0 + d) for d in range(dim)], per)
+        fn_host = t.interpolate(f if fields > 1 else f[0])
+        fn_dev = t.interpolate(torch.from_numpy(f if fields > 1 else f[0]).cuda())
+        for k in range(fields):
+            o = OracleSpline(order, shape, per, lo=[0.0] * dim, hi=[1.0 + d for d in range(dim)], f=f[k])
+            ref = o.control_points()
+            assert np.array_equal(fn_host.control_points(field=k), ref), (shape, per, k)
+            assert np.array_equal(fn_dev.control_points(field=k), ref), (shape, per, k)
+    # float
+    f32 = rng.standard_normal((66, 70, 72)).astype(np.float32)
+    fn32 = pkg.InterpolationFunction(order, f32, [(0.0, 1.0)] * 3, dtype=np.float32)
+    ref = OracleSpline(order, (66, 70, 72), [False] * 3, lo=[0.0] * 3, hi=[1.0] * 3, f=f32.astype(np.float64)).control_points()
+    assert np.abs(fn32.control_points() - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
 @pytest.mark.parametrize("order,periodic", [(1, True), (2, False), (3, False), (3, True), (4, True), (5, False), (5, True)])
 def test_chunk_parallel_solve_long_lines(pkg, order, periodic):
     """Few, long lines take the chunk-parallel sweep (warm-up window instead of the sequential
