@@ -441,21 +441,46 @@ def test_baseline_cfg1_2d_cubic_1024(pkg):
 
 
 def test_baseline_cfg2_1d_quintic_periodic_long(pkg):
-    """BASELINE configs[1] scaled to 2^21 mesh points (the oracle's serial LU bounds the size):
-    1-D order-5 periodic, value + first derivative, chunk-parallel solve.  A long axis is where
-    rounded knot values matter most: the tolerance is still 1e-12."""
+    """BASELINE configs[1] at full size: 1-D order-5 periodic, 2^24 mesh points, value + first
+    derivative; compact LU factors (bspl_host.h) and the chunk-parallel solve.  A long axis is
+    where rounded knot values matter most: spans exact, tolerance still 1e-12."""
     rng = np.random.default_rng(7)
-    n = 1 << 21
+    n = 1 << 24
     f = np.sin(np.arange(n) * (14 * np.pi / n)) + 0.1 * rng.standard_normal(n)
     o = OracleSpline(5, (n,), [1], lo=[0.0], hi=[1.0], f=f)
     fn = pkg.InterpolationFunction(5, f, [(0.0, 1.0)], [True])
+    assert np.array_equal(fn.knots(0), o.knots(0))
     c, ref = fn.control_points(), o.control_points()
     assert np.abs(c - ref).max() <= 1e-13 * np.abs(ref).max()
+    assert (c != ref).mean() < 1e-3
     pts = rng.uniform(-0.5, 1.5, 1 << 20)  # includes wrapped queries
     assert np.array_equal(fn.locate(pts)[:, 0], o.spans(pts)[:, 0])
     vg = fn.value_grad(pts)
     _close(vg[:, 0], o.eval(pts, 8))
     _close(vg[:, 1], o.deriv(pts, [1], 8))
+    idx = rng.integers(0, n, 100000)
+    assert np.abs(fn(idx / n) - f[idx]).max() <= 1e-12 * np.abs(f).max()   # reproduces its data
+
+
+@pytest.mark.parametrize("periodic", [False, True])
+def test_baseline_cfg4_3d_cubic_512_solve(pkg, periodic):
+    """BASELINE configs[3] at full size: the 512^3 cubic control-point solve (TMA-tiled contiguous
+    sweep + two strided sweeps; transposing route when periodic).  Control points bit-identical to
+    the oracle's sequential solve, and the spline reproduces its data at the mesh nodes."""
+    import torch
+    rng = np.random.default_rng(512 + periodic)
+    shape = (512, 512, 512)
+    f = rng.standard_normal(shape)
+    per = [periodic] * 3
+    o = OracleSpline(3, shape, per, lo=[0, 0, 0], hi=[1, 1, 1], f=f, nthreads=8)
+    fn = pkg.InterpolationFunction(3, torch.from_numpy(f).cuda(), [(0.0, 1.0)] * 3, per)
+    assert np.array_equal(fn.control_points(), o.control_points())
+    idx = rng.integers(0, 512, size=(50000, 3))
+    nodes = idx / (512.0 if periodic else 511.0)
+    assert np.abs(fn(nodes) - f[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f).max()
+    pts = rng.uniform(0, 1, (1 << 16, 3))
+    assert np.array_equal(fn.locate(pts), o.spans(pts))
+    _close(fn(pts), o.eval(pts, 8))
 
 
 def test_baseline_cfg3_3d_cubic_256_sample(pkg):
