@@ -110,12 +110,13 @@ cudaError_t launch_sweep(const AxisLU<R>& lu, const SweepGeom& g, R* data, const
 
 // First sweep of the separable solve fused with the copy out of the caller's mesh: lines along
 // the contiguous axis are read from `src` (line space strides src_ms, same extents g.m) and the
-// solved lines land in `dst` (geometry g), shifted cyclically by shift[k] along g.m[k]
+// solved lines land in `dst` (geometry g), shifted cyclically by shift[k] along g.m[k] and, when
+// `rotate` is set (periodic line axis), by the band width along the line itself
 // (InterpolationTemplate.hpp:451-462).  cudaErrorNotSupported: geometry not addressable by TMA
-// (odd strides, shift along g.m[2]) -- the caller takes another route.
+// (odd strides, unaligned base) -- the caller takes another route.
 template <typename R>
 cudaError_t launch_sweep_contig_from(const AxisLU<R>& lu, const SweepGeom& g, const R* src, const long long* src_ms,
-                                     const int* shift, R* dst, cudaStream_t s);
+                                     const int* shift, int rotate, R* dst, cudaStream_t s);
 
 // f (compact, [fields][n0][n1][n2]) -> padded coefficient array, rotating each
 // periodic axis by +shift[d] (InterpolationTemplate.hpp:451-462).

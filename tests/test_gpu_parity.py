@@ -318,15 +318,18 @@ def test_binned_tma_path_matches_direct_and_oracle(pkg, order, periodic):
 @pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
 def test_tma_tiled_contiguous_sweep_bit_exact(pkg, order):
     """>= 4096 lines along the contiguous axis take the TMA-tiled sweep (bspl_solve.cu): fused with
-    the copy out of the caller's mesh when the last two axes carry no cyclic shift, in place
-    otherwise; ragged tiles (70 lines per run, 72 = 4.5 tile rows), a shifted slow axis, many
-    fields, host and device meshes, and an odd row length that TMA cannot address (falls back).
+    the copy out of the caller's mesh, cyclic shifts of periodic axes applied to the tile
+    coordinates (wrapped rows patched in) and along the line (delay of the right-hand side);
+    ragged tiles (70 lines per run, 72 = 4.5 tile rows), many fields, host and device meshes, and
+    an odd row length that TMA cannot address (falls back).
     Control points bit-identical to the oracle's sequential solve in every case."""
     import torch
     rng = np.random.default_rng(4200 + order)
     cases = [((66, 70, 72), [False, False, False]), ((66, 70, 72), [True, False, False]),
-             ((66, 70, 72), [False, True, True]), ((66, 70, 73), [False, False, False]),
-             ((260, 48), [False, False])]
+             ((66, 70, 72), [False, True, True]), ((66, 70, 72), [True, True, True]),
+             ((66, 70, 72), [False, False, True]), ((66, 70, 72), [False, True, False]),
+             ((66, 70, 73), [False, False, False]), ((260, 48), [False, False]), ((260, 48), [True, True]),
+             ((130, 40), [False, True])]
     for shape, per in cases:
         dim = len(shape)
         fields = 20 if dim == 2 else 1
