@@ -131,17 +131,22 @@ class ShardedSolve3D:
             return torch.roll(x, shifts=self.order // 2, dims=axis)
         return x
 
+    def _local_sweeps(self, f_slab):
+        """Working copy of the slab (periodic axes 1, 2 rotated) with axis 2 solved: lines along the
+        contiguous axis go through the TMA-tiled sweep (bspl_solve.cu) in place."""
+        n0, n1, n2 = self.shape
+        w = self._shift(self._shift(f_slab, 2), 1)
+        w = w.clone() if w.data_ptr() == f_slab.data_ptr() else w.contiguous()
+        self.template.sweep_axis(2, w, (1, f_slab.shape[0], n1), (0, n1 * n2, n2), 1)
+        return w
+
     def solve(self, f_slab, back_to_axis0=False):
         """f_slab: CUDA tensor [n0_loc, n1, n2], this rank's axis-0 slab of the mesh.
         Returns the control points as a slab of axis 1, [n0, n1_loc, n2] (or of axis 0)."""
         n0, n1, n2 = self.shape
         n0_loc = f_slab.shape[0]
         t = self.template
-        # A thread-per-line sweep along the contiguous axis cannot be coalesced: sweep axis 2 in a
-        # transposed copy [n0_loc][n2][n1] (lines of stride n1), then transpose back for axis 1.
-        wt = self._shift(self._shift(f_slab, 2), 1).transpose(1, 2).contiguous()
-        t.sweep_axis(2, wt, (1, n0_loc, n1), (0, n1 * n2, 1), n1)
-        w = wt.transpose(1, 2).contiguous()
+        w = self._local_sweeps(f_slab)
         t.sweep_axis(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2)
         y = reshard_axis0_to_axis1(w, n0, self.group)
         y = self._shift(y, 0).contiguous()
@@ -215,9 +220,7 @@ class ShardedSolve3D:
         x0 = shard_range(n0, rank, world)[0]
         s1 = shard_sizes(n1, world)
         t = self.template
-        wt = self._shift(self._shift(f_slab, 2), 1).transpose(1, 2).contiguous()
-        t.sweep_axis(2, wt, (1, n0_loc, n1), (0, n1 * n2, 1), n1)
-        w = wt.transpose(1, 2).contiguous()
+        w = self._local_sweeps(f_slab)
         if world > 1:
             # stream-ordered barrier (a one-element NCCL all-reduce, no host synchronisation): every
             # rank has consumed its previous result before anyone overwrites the buffers
