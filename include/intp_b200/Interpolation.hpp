@@ -15,6 +15,7 @@
 #define INTP_B200_INTERPOLATION_HPP
 
 #include <array>
+#include <cstring>
 #include <cstddef>
 #include <cstdint>
 #include <iterator>
@@ -146,6 +147,34 @@ template <typename T> constexpr bspl_dtype dtype_of() {
     return std::is_same_v<T, double> ? BSPL_F64 : BSPL_F32;
 }
 
+// Vector-valued T (e.g. the reference's Vec<2, float> circle, interpolation-test.cpp:674-703): any
+// trivially copyable aggregate of K values of the coordinate type U is carried as K fields of one
+// function -- K independent scalar splines sharing knots, factors and query work.
+template <typename T, typename U>
+struct components_of {
+    static_assert(std::is_arithmetic_v<T> ? std::is_same_v<T, U>
+                                          : (std::is_trivially_copyable_v<T> && sizeof(T) % sizeof(U) == 0),
+                  "T must be the coordinate type U or a trivially copyable aggregate of U values");
+    static constexpr std::size_t value = sizeof(T) / sizeof(U);
+};
+// [m][K] interleaved -> [K][m]
+template <typename T, typename U>
+std::vector<U> split_components(const T* data, std::size_t m) {
+    constexpr std::size_t K = components_of<T, U>::value;
+    std::vector<U> out(K * m);
+    const U* in = reinterpret_cast<const U*>(data);
+    for (std::size_t i = 0; i < m; ++i)
+        for (std::size_t k = 0; k < K; ++k) out[k * m + i] = in[i * K + k];
+    return out;
+}
+// [m] values of component k -> slot k of [m][stride / K ...] interleaved storage
+template <typename T, typename U>
+void merge_component(const U* field, std::size_t m, std::size_t k, T* data) {
+    constexpr std::size_t K = components_of<T, U>::value;
+    U* out = reinterpret_cast<U*>(data);
+    for (std::size_t i = 0; i < m; ++i) out[i * K + k] = field[i];
+}
+
 struct FnDeleter { void operator()(bspl_function* p) const { bspl_function_destroy(p); } };
 struct PlanDeleter { void operator()(bspl_query_plan* p) const { bspl_query_plan_destroy(p); } };
 struct TmDeleter { void operator()(bspl_template* p) const { bspl_template_destroy(p); } };
@@ -201,15 +230,31 @@ class EvalProxy {
     }
     // single point, like the reference's closure: proxy(interp) -> value
     T operator()(const function_type& interp) const {
-        T v{};
-        b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, &v, 0, nullptr));
+        constexpr std::size_t K = b200_detail::components_of<T, U>::value;
+        U buf[K];
+        for (std::size_t k = 0; k < K; ++k)
+            b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), static_cast<int64_t>(k), nullptr, 0,
+                                                        &buf[k], 0, nullptr));
+        T v;
+        std::memcpy(&v, buf, sizeof(T));
         return v;
     }
     // batched: out[q]
     void operator()(const function_type& interp, T* out) const {
-        b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, out, 0, nullptr));
+        constexpr std::size_t K = b200_detail::components_of<T, U>::value;
+        if constexpr (K == 1) {
+            b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, out, 0, nullptr));
+        } else {
+            std::vector<U> tmp(q_);
+            for (std::size_t k = 0; k < K; ++k) {
+                b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), static_cast<int64_t>(k), nullptr, 0,
+                                                            tmp.data(), 0, nullptr));
+                b200_detail::merge_component<T, U>(tmp.data(), q_, k, out);
+            }
+        }
     }
     void value_grad(const function_type& interp, T* out) const {
+        static_assert(b200_detail::components_of<T, U>::value == 1, "value_grad: scalar functions only");
         b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 1, out, 0, nullptr));
     }
     std::size_t size() const { return q_; }
@@ -222,7 +267,6 @@ class EvalProxy {
 // ---------------------------------------------------------------- InterpolationFunction
 template <typename T, std::size_t D, std::size_t O, typename U = double>
 class InterpolationFunction {
-    static_assert(std::is_same_v<T, U>, "the B200 build evaluates real splines with T == U");
     static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..3, order 0..5");
 
    public:
@@ -231,6 +275,8 @@ class InterpolationFunction {
     using size_type = std::size_t;
     static constexpr size_type dim = D;
     static constexpr size_type order = O;
+    // scalar T: 1; vector-valued T: number of U values it holds (one field each)
+    static constexpr size_type components = b200_detail::components_of<T, U>::value;
     template <typename V> using DimArray = std::array<V, D>;
     friend class InterpolationFunctionTemplate<T, D, O, U>;
 
@@ -279,25 +325,15 @@ class InterpolationFunction {
     template <typename... Coords, typename = std::enable_if_t<sizeof...(Coords) == D &&
                                                               (std::is_arithmetic_v<Coords> && ...)>>
     val_type operator()(Coords... x) const { return (*this)(DimArray<coord_type>{static_cast<coord_type>(x)...}); }
-    val_type operator()(DimArray<coord_type> coord) const {
-        val_type v{};
-        b200_detail::check(bspl_evaluate(need(), 0, coord.data(), 1, nullptr, &v, 0, nullptr));
-        return v;
-    }
-    val_type at(DimArray<coord_type> coord) const {
-        val_type v{};
-        b200_detail::check(bspl_evaluate_at(need(), 0, coord.data(), 1, nullptr, &v, nullptr));
-        return v;
-    }
+    val_type operator()(DimArray<coord_type> coord) const { return one(coord.data(), nullptr, false); }
+    val_type at(DimArray<coord_type> coord) const { return one(coord.data(), nullptr, true); }
     template <typename... Coords, typename = std::enable_if_t<sizeof...(Coords) == D &&
                                                               (std::is_arithmetic_v<Coords> && ...)>>
     val_type at(Coords... x) const { return at(DimArray<coord_type>{static_cast<coord_type>(x)...}); }
 
     val_type derivative(DimArray<coord_type> coord, DimArray<size_type> derivatives) const {
         const auto dv = to_int(derivatives);
-        val_type v{};
-        b200_detail::check(bspl_evaluate(need(), 0, coord.data(), 1, dv.data(), &v, 0, nullptr));
-        return v;
+        return one(coord.data(), dv.data(), false);
     }
     template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (std::is_integral_v<Args> && ...)>>
     val_type derivative(DimArray<coord_type> coord, Args... deri) const {
@@ -311,9 +347,7 @@ class InterpolationFunction {
     }
     val_type derivative_at(DimArray<coord_type> coord, DimArray<size_type> derivatives) const {
         const auto dv = to_int(derivatives);
-        val_type v{};
-        b200_detail::check(bspl_evaluate_at(need(), 0, coord.data(), 1, dv.data(), &v, nullptr));
-        return v;
+        return one(coord.data(), dv.data(), true);
     }
     template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (std::is_integral_v<Args> && ...)>>
     val_type derivative_at(DimArray<coord_type> coord, Args... deri) const {
@@ -328,26 +362,36 @@ class InterpolationFunction {
 
     // ---- batched entry points (new).  Host pointers: synchronous.  Device pointers: enqueued on
     // `stream` (a cudaStream_t), no synchronisation.
-    void evaluate(const coord_type* points, size_type q, val_type* out) const {
-        b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), nullptr, out, 0, nullptr));
-    }
+    void evaluate(const coord_type* points, size_type q, val_type* out) const { many(points, q, nullptr, out); }
     void evaluate(const std::vector<DimArray<coord_type>>& points, std::vector<val_type>& out) const {
         out.resize(points.size());
         evaluate(points.empty() ? nullptr : points.front().data(), points.size(), out.data());
     }
     void evaluate(const coord_type* points, size_type q, DimArray<size_type> derivatives, val_type* out) const {
         const auto dv = to_int(derivatives);
-        b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), dv.data(), out, 0, nullptr));
+        many(points, q, dv.data(), out);
     }
     // out[q][1 + D] = value, d/dx0, ..., d/dx(D-1)
     void evaluate_value_grad(const coord_type* points, size_type q, val_type* out) const {
-        b200_detail::check(bspl_evaluate_value_grad(need(), 0, points, static_cast<int64_t>(q), out, 0, nullptr));
+        if constexpr (components == 1) {
+            b200_detail::check(bspl_evaluate_value_grad(need(), 0, points, static_cast<int64_t>(q), out, 0, nullptr));
+        } else {
+            std::vector<coord_type> tmp(q * (1 + D));
+            for (size_type k = 0; k < components; ++k) {
+                b200_detail::check(bspl_evaluate_value_grad(need(), static_cast<int64_t>(k), points, static_cast<int64_t>(q),
+                                                            tmp.data(), 0, nullptr));
+                b200_detail::merge_component<T, U>(tmp.data(), q * (1 + D), k, out);
+            }
+        }
     }
+    // device pointers: scalar functions; for vector-valued T evaluate field k with the C ABI (handle())
     void evaluate_device(const coord_type* d_points, size_type q, val_type* d_out, void* stream = nullptr) const {
+        static_assert(components == 1, "device-pointer evaluation: scalar functions only");
         b200_detail::check(bspl_evaluate(need(), 0, d_points, static_cast<int64_t>(q), nullptr, d_out, 1, stream));
     }
     void evaluate_value_grad_device(const coord_type* d_points, size_type q, val_type* d_out,
                                     void* stream = nullptr) const {
+        static_assert(components == 1, "device-pointer evaluation: scalar functions only");
         b200_detail::check(bspl_evaluate_value_grad(need(), 0, d_points, static_cast<int64_t>(q), d_out, 1, stream));
     }
 
@@ -369,7 +413,15 @@ class InterpolationFunction {
         typename MeshDimension<D>::index_type ext{};
         for (size_type d = 0; d < D; ++d) ext[d] = n_[d];
         Mesh<T, D> m{MeshDimension<D>(ext)};
-        b200_detail::check(bspl_function_control_points(need(), 0, m.data()));
+        if constexpr (components == 1) {
+            b200_detail::check(bspl_function_control_points(need(), 0, m.data()));
+        } else {
+            std::vector<coord_type> tmp(m.size());
+            for (size_type k = 0; k < components; ++k) {
+                b200_detail::check(bspl_function_control_points(need(), static_cast<int64_t>(k), tmp.data()));
+                b200_detail::merge_component<T, U>(tmp.data(), m.size(), k, const_cast<T*>(m.data()));
+            }
+        }
         return m;
     }
     std::vector<coord_type> knots(size_type d) const {
@@ -384,6 +436,31 @@ class InterpolationFunction {
     const bspl_function* need() const {
         if (!h_) throw std::runtime_error("empty InterpolationFunction (populate it with a template's interpolate())");
         return h_.get();
+    }
+    // one point: component k is field k
+    val_type one(const coord_type* c, const int* dv, bool checked) const {
+        coord_type buf[components];
+        for (size_type k = 0; k < components; ++k) {
+            if (checked)
+                b200_detail::check(bspl_evaluate_at(need(), static_cast<int64_t>(k), c, 1, dv, &buf[k], nullptr));
+            else
+                b200_detail::check(bspl_evaluate(need(), static_cast<int64_t>(k), c, 1, dv, &buf[k], 0, nullptr));
+        }
+        val_type v;
+        std::memcpy(&v, buf, sizeof(val_type));
+        return v;
+    }
+    void many(const coord_type* points, size_type q, const int* dv, val_type* out) const {
+        if constexpr (components == 1) {
+            b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), dv, out, 0, nullptr));
+        } else {
+            std::vector<coord_type> tmp(q);
+            for (size_type k = 0; k < components; ++k) {
+                b200_detail::check(bspl_evaluate(need(), static_cast<int64_t>(k), points, static_cast<int64_t>(q), dv,
+                                                 tmp.data(), 0, nullptr));
+                b200_detail::merge_component<T, U>(tmp.data(), q, k, out);
+            }
+        }
     }
     static std::array<int, D> to_int(const DimArray<size_type>& a) {
         std::array<int, D> r{};
@@ -446,7 +523,7 @@ class InterpolationFunctionTemplate {
                                          std::to_string(d));
         }
         bspl_template* t = nullptr;
-        b200_detail::check(bspl_template_create(b200_detail::dtype_of<T>(), static_cast<int>(D), static_cast<int>(O), n, per,
+        b200_detail::check(bspl_template_create(b200_detail::dtype_of<U>(), static_cast<int>(D), static_cast<int>(O), n, per,
                                                 lo, hi, coords, b200_detail::default_device(), &t));
         h_.reset(t);
     }
@@ -467,7 +544,13 @@ class InterpolationFunctionTemplate {
     function_type interpolate(const Mesh<T, D>& f_mesh) const {
         check_mesh(f_mesh);
         bspl_function* f = nullptr;
-        b200_detail::check(bspl_template_interpolate(h_.get(), f_mesh.data(), 1, 0, nullptr, &f));
+        constexpr size_type K = b200_detail::components_of<T, U>::value;
+        if constexpr (K == 1) {
+            b200_detail::check(bspl_template_interpolate(h_.get(), f_mesh.data(), 1, 0, nullptr, &f));
+        } else {  // K fields, one per component
+            const std::vector<U> fields = b200_detail::split_components<T, U>(f_mesh.data(), f_mesh.size());
+            b200_detail::check(bspl_template_interpolate(h_.get(), fields.data(), static_cast<int64_t>(K), 0, nullptr, &f));
+        }
         return function_type(b200_detail::FnHandle(f));
     }
     template <typename It, size_type DD = D, typename = std::enable_if_t<DD == 1>>
@@ -478,11 +561,19 @@ class InterpolationFunctionTemplate {
     void interpolate(function_type& interp, const Mesh<T, D>& f_mesh) const {
         check_mesh(f_mesh);
         if (!interp.h_) { interp = interpolate(f_mesh); return; }
-        b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), f_mesh.data(), 1, 0, nullptr));
+        constexpr size_type K = b200_detail::components_of<T, U>::value;
+        if constexpr (K == 1) {
+            b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), f_mesh.data(), 1, 0, nullptr));
+        } else {
+            const std::vector<U> fields = b200_detail::split_components<T, U>(f_mesh.data(), f_mesh.size());
+            b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), fields.data(),
+                                                              static_cast<int64_t>(K), 0, nullptr));
+        }
         interp.cache_info();
     }
     // device-resident mesh (row-major, same shape), enqueued on `stream`
     function_type interpolate_device(const T* d_mesh, void* stream = nullptr) const {
+        static_assert(b200_detail::components_of<T, U>::value == 1, "device meshes: scalar T (pass K fields through the C ABI)");
         bspl_function* f = nullptr;
         b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
         return function_type(b200_detail::FnHandle(f));

@@ -155,6 +155,40 @@ int main() {
         }
         expect(err < 2e-4f, "float periodic cubic on cos", err);
     }
+    // vector-valued T (interpolation-test.cpp:674-703: a circle as Vec<2, float>): carried as two fields
+    {
+        struct Vec2f { float x, y; };
+        constexpr std::size_t n = 31;
+        const float two_pi = 2.f * 3.14159265358979f;
+        std::vector<Vec2f> pts;
+        std::vector<float> xs, ys;
+        for (std::size_t i = 0; i < n; ++i) {
+            pts.push_back({std::cos(two_pi * float(i) / n), std::sin(two_pi * float(i) / n)});
+            xs.push_back(pts.back().x); ys.push_back(pts.back().y);
+        }
+        InterpolationFunction1D<3, Vec2f, float> circ(std::make_pair(0.f, two_pi), util::get_range(pts), true);
+        InterpolationFunction1D<3, float, float> cx(std::make_pair(0.f, two_pi), util::get_range(xs), true);
+        InterpolationFunction1D<3, float, float> cy(std::make_pair(0.f, two_pi), util::get_range(ys), true);
+        float err = 0;
+        bool same = true;
+        std::vector<std::array<float, 1>> q;
+        for (std::size_t i = 0; i < 257; ++i) {
+            const float th = two_pi * float(i) / 257;
+            q.push_back({th});
+            const Vec2f v = circ(th);
+            err = std::max(err, std::max(std::abs(v.x - std::cos(th)), std::abs(v.y - std::sin(th))));
+            same = same && v.x == cx(th) && v.y == cy(th);
+            const Vec2f d = circ.derivative({th}, 1);
+            same = same && d.x == cx.derivative({th}, 1) && d.y == cy.derivative({th}, 1);
+        }
+        std::vector<Vec2f> batch;
+        circ.evaluate(q, batch);
+        for (std::size_t i = 0; i < q.size(); ++i) same = same && batch[i].x == cx(q[i][0]) && batch[i].y == cy(q[i][0]);
+        const auto ctrl = circ.control_points();
+        const auto ctrl_x = cx.control_points();
+        for (std::size_t i = 0; i < n; ++i) same = same && ctrl(i).x == ctrl_x(i);
+        expect(err < 2e-4f && same && decltype(circ)::components == 2, "Vec2f periodic cubic circle (two fields)", err);
+    }
     std::printf("%d failure(s)\n", failures);
     return failures;
 }
