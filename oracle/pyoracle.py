@@ -31,7 +31,7 @@ def build(ref="/root/reference", force=False):
         for n in ("libintp_ref_cell.so", "libintp_ref_plain.so", "libintp_ref_plain_mt.so"):
             need = need or not os.path.exists(os.path.join(OUT, n))
     if need:
-        args = ["make", "-f", os.path.join(HERE, "Makefile"), "all", "REF=" + ref]
+        args = ["make", "-j4", "-f", os.path.join(HERE, "Makefile"), "all", "REF=" + ref]
         if force:
             args.insert(1, "-B")
         subprocess.check_call(args, cwd=HERE)
