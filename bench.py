@@ -123,7 +123,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "Mpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -384,7 +384,7 @@ def run_gpu(args):
             "solve": solve,
             "checksum": checksum,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -401,10 +401,27 @@ def main():
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    # stdout carries the one JSON line and nothing else: whatever libraries print while the run is
+    # in progress (NCCL's version banner, compiler chatter of the CPU checker) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
         run_gpu(args)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the result line on the process's original stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
