@@ -517,6 +517,33 @@ def test_baseline_cfg3_3d_cubic_256_sample(pkg):
     assert np.abs(fn(nodes) - f[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f).max()
 
 
+def test_more_than_2_28_queries_are_sliced(pkg):
+    """Maximum sizes: the query sort needs 32 bytes of scratch per query, so batches beyond 2^28
+    queries run in slices (bspl_capi.cu: launch_eval).  2^28 + 12 345 device-resident queries; a
+    sample from every slice, the tail slice included, must equal a small direct evaluation."""
+    import torch
+    if torch.cuda.mem_get_info()[0] < 40 * (1 << 30):
+        pytest.skip("needs ~25 GB of device memory")
+    rng = np.random.default_rng(2828)
+    shape = (64, 64, 64)
+    fn = pkg.InterpolationFunction(3, smooth_field(shape, rng), [(0.0, 1.0)] * 3)
+    q = (1 << 28) + 12345
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    pts = torch.rand((q, 3), dtype=torch.float64, device="cuda", generator=gen)
+    out = fn.evaluate(pts)
+    idx = torch.cat([torch.randint(0, q, (200000,), device="cuda", generator=gen),
+                     torch.arange(q - 12345, q, device="cuda")])
+    sample = pts[idx].contiguous()
+    try:
+        pkg.set_eval_path("direct")
+        ref = fn.evaluate(sample)
+    finally:
+        pkg.set_eval_path("auto")
+    assert (out[idx] - ref).abs().max().item() <= 1e-13 * ref.abs().max().item()
+    del pts, out
+    torch.cuda.empty_cache()
+
+
 def test_vector_valued_circle_as_two_fields(pkg):
     """interpolation-test.cpp:674-703 (T = Vec<2,float>, U = float): a closed curve interpolated
     componentwise; here the components are the fields of one handle sharing one query set."""
