@@ -61,3 +61,11 @@ def all_combos(dims=(1, 2, 3), orders=range(6)):
         for order in orders:
             for per in itertools.product([False, True], repeat=dim):
                 yield dim, order, per
+
+
+def long_axis_field(n):
+    """Exactly representable pseudo-random data in [-1, 1) (an integer hash of the index): identical
+    on every platform, so tests/golden/ref_outputs_long.npz stores only the reference's outputs."""
+    i = np.arange(n, dtype=np.uint64)
+    h = (i * np.uint64(2654435761) + np.uint64(12345)) & np.uint64(0xFFFFFFFF)
+    return (h.astype(np.float64) - 2147483648.0) / 2147483648.0

@@ -184,6 +184,36 @@ def test_committed_reference_outputs_fp32(pkg):
         assert np.abs(got - dvals).max() <= tol * np.abs(dvals).max()
 
 
+def test_long_axis_compact_factors_match_committed_reference_outputs(pkg):
+    """tests/golden/ref_outputs_long.npz (the unmodified reference on a 16 411-point uniform axis): such
+    axes are factored in compact form (both ends on a surrogate, one steady row in between,
+    bspl_host.h) and solved by the chunk-parallel sweep.  Spans exact, control points to 1e-13
+    (bit-identical but for isolated last-bit ties), values to 1e-12."""
+    import os
+    from cases import long_axis_field
+    from conftest import ROOT
+    d = np.load(os.path.join(ROOT, "tests", "golden", "ref_outputs_long.npz"))
+    n = int(d["n"])
+    f = long_axis_field(n)
+    for c in range(int(d["n_cases"])):
+        order, per = int(d["c%d_order" % c]), bool(d["c%d_periodic" % c])
+        fn = pkg.InterpolationFunction(order, f, [(-1.5, 2.25)], [per])
+        ctrl, ref = fn.control_points(), d["c%d_ctrl" % c]
+        assert np.abs(ctrl - ref).max() <= 1e-13 * np.abs(ref).max(), (order, per)
+        assert (ctrl != ref).mean() < 1e-3
+        pts = d["c%d_pts" % c]
+        assert np.array_equal(fn.locate(pts).reshape(-1), d["c%d_spans" % c].reshape(-1))
+        _close(fn(pts), d["c%d_vals" % c], 1e-11 if per else 1e-12)   # wrapped / extrapolated points included
+    # the same axis inside a 2-D mesh (48 strided lines of 16 411 points)
+    t = pkg.InterpolationFunctionTemplate(3, (n, 48), [(-1.5, 2.25), (0.0, 1.0)], [False, False])
+    g = np.outer(f, np.ones(48))   # every column of the mesh is the 1-D data
+    fn2 = t.interpolate(g)
+    # axis 1 (constant data along a clamped cubic axis) reproduces the constant, so column k equals the 1-D control points
+    ref3 = d["c0_ctrl"]
+    got = fn2.control_points()
+    assert np.abs(got[:, 7] - ref3).max() <= 1e-12 * np.abs(ref3).max()
+
+
 def test_band_solver(pkg):
     """band-matrix-and-solver-test.cpp: ||b - A x|| / ||b|| < 1e-10, and bit parity with the oracle."""
     from test_oracle import _band_matrices

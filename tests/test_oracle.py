@@ -199,3 +199,19 @@ def test_committed_reference_outputs():
         assert np.array_equal(o.eval(pts), data["c%d_vals" % c])
         dv = [int(v) for v in data["c%d_dv" % c]]
         assert np.array_equal(o.deriv(pts, dv), data["c%d_dvals" % c])
+
+
+def test_long_uniform_axis_matches_committed_reference_outputs():
+    """tests/golden/ref_outputs_long.npz: the unmodified reference on a 16 411-point axis."""
+    from cases import long_axis_field
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_outputs_long.npz"))
+    n = int(d["n"])
+    f = long_axis_field(n)
+    for c in range(int(d["n_cases"])):
+        order, per = int(d["c%d_order" % c]), bool(d["c%d_periodic" % c])
+        o = OracleSpline(order, (n,), [per], lo=[-1.5], hi=[2.25], f=f)
+        assert np.array_equal(o.control_points(), d["c%d_ctrl" % c])
+        pts = d["c%d_pts" % c]
+        assert np.array_equal(o.spans(pts).reshape(-1), d["c%d_spans" % c].reshape(-1))
+        ref = d["c%d_vals" % c]
+        assert np.abs(o.eval(pts) - ref).max() <= 1e-13 * np.abs(ref).max()
