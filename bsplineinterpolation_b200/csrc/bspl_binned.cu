@@ -204,10 +204,16 @@ __device__ __forceinline__ int axis_weights_interior(const AxisParams<R>& a, R x
     constexpr int WIN = 2 * O > 0 ? 2 * O : 1;
     R fs;
     const int span = locate_uniform_interior<R, O>(a, x, fs);
-    R tk[WIN];
-    uniform_knot_window<R, O>(a, fs, tk);
-    if (GRAD || k == 0) basis_uniform<R, O, GRAD>(tk, x, a.inv_dx, w, dw);
-    else deriv_weights<R, O>(tk, x, k, w);
+    if (GRAD || k == 0) {
+        // the span is exact (compared against the reference's knot values); the weights only need
+        // the offset inside the cell
+        const R u = (x - uniform_knot<R>(a, fs)) * a.inv_dx;
+        basis_unit<R, O, GRAD>(u, a.inv_dx, w, dw);
+    } else {
+        R tk[WIN];
+        uniform_knot_window<R, O>(a, fs, tk);
+        deriv_weights<R, O>(tk, x, k, w);
+    }
     return span - O;
 }
 
@@ -231,7 +237,9 @@ __global__ void __launch_bounds__(kEvalThreads, 2)
     constexpr int NOUT = GRAD ? 4 : 1;
     constexpr bool DUAL = dual_brick<O>();
     constexpr uint32_t kBrickBytes = BE * BE * BP * sizeof(R);
-    constexpr uint32_t kBrickStride = (kBrickBytes + 127) / 128 * 128;
+    // the shifted copy starts half the banks further, so that z offsets 2k and 2k+1 (same chunk index, one
+    // in each copy) do not collide
+    constexpr uint32_t kBrickStride = (kBrickBytes + 127) / 128 * 128 + 64;
     using R2 = typename std::conditional<sizeof(R) == 8, double2, float2>::type;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     R* brick = reinterpret_cast<R*>(smem_raw);
@@ -404,7 +412,7 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, int pha
     ep.rec = static_cast<const Rec<R>*>(sc.rec); ep.out = a.out; ep.work = sc.work; ep.n_work = sc.n_work;
     ep.next_item = sc.next_item;
     constexpr int kOne = (BE * BE * BP * int(sizeof(R)) + 127) / 128 * 128;
-    constexpr int smem = dual_brick<O>() ? 2 * kOne : kOne;
+    constexpr int smem = dual_brick<O>() ? 2 * kOne + 64 : kOne;
     if (a.mode == kValueGrad) {
         auto k = eval_binned_kernel<R, O, true>;
         e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

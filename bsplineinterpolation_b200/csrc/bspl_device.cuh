@@ -254,6 +254,44 @@ __device__ __forceinline__ void basis_uniform(const R* tk, R x, R inv_dx, R* w, 
     basis_level<R, O>(tk, x, O, inv, w);
 }
 
+// Cox-de Boor on the unit-spaced knots of a uniform interior cell.  With u = (x - t[span]) / dx
+// the local knots are the integers, every denominator of level j is exactly j, and the triangle
+// needs no knot values and no reciprocals: N[r] <- saved + (r+1-u) * N[r]/j, saved <- (u+j-r-1) * N[r]/j.
+// w[r] weights control point span - O + r; dw = d w / d x = (N'[r-1] - N'[r]) / dx from the
+// level-(O-1) values N'.  Agrees with the knot-based triangle to a few ulp * (|t| / dx).
+template <typename R, int O, bool GRAD>
+__device__ __forceinline__ void basis_unit(R u, R inv_dx, R* w, R* dw) {
+#pragma unroll
+    for (int i = 0; i <= O; ++i) { w[i] = R(0); if (GRAD) dw[i] = R(0); }
+    // N[0..j] after level j, kept left-aligned while building, moved right-aligned at the end
+    R N[O + 1];
+    N[0] = R(1);
+#pragma unroll
+    for (int j = 1; j <= O; ++j) {
+        if (GRAD && j == O) {
+            // N holds the level-(O-1) values N'[0..O-1] of functions span-O+1 .. span
+#pragma unroll
+            for (int r = 0; r <= O; ++r) {
+                R v = R(0);
+                if (r >= 1) v = N[r - 1];
+                if (r <= O - 1) v -= N[r];
+                dw[r] = v * inv_dx;
+            }
+        }
+        const R inv_j = R(1) / R(j);  // compile-time constant after unrolling
+        R saved = R(0);
+#pragma unroll
+        for (int r = 0; r < j; ++r) {
+            const R temp = N[r] * inv_j;
+            N[r] = fma(R(r + 1) - u, temp, saved);
+            saved = (u + R(j - r - 1)) * temp;
+        }
+        N[j] = saved;
+    }
+#pragma unroll
+    for (int r = 0; r <= O; ++r) w[r] = N[r];
+}
+
 // base_spline_value (BSpline.hpp:83-111): Cox-de Boor triangle of order `so`
 // (so <= O), result right-aligned in b[0..O].
 template <typename R, int O>
