@@ -26,6 +26,13 @@ B.InterpolationFunction(3, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, 
 B.InterpolationFunction(3, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, [True, False, False])
 B.InterpolationFunction(5, rng.standard_normal((66, 70, 72)).astype(np.float32), [(0.0, 1.0)] * 3, dtype=np.float32)
 B.InterpolationFunction(3, rng.standard_normal((66, 70, 73)), [(0.0, 1.0)] * 3, [False, False, False])
+# periodic axes through the fused sweep: wrapped rows patched in, line rotation by the delay registers
+B.InterpolationFunction(3, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, [True, True, True])
+B.InterpolationFunction(4, rng.standard_normal((66, 70, 72)), [(0.0, 1.0)] * 3, [False, True, True])
+B.InterpolationFunction(5, rng.standard_normal((20, 260, 48)), [(0.0, 1.0)] * 3, [True, False, True])
+# compact factors (axis of 20 000 points) with the chunk-parallel and the strided sweeps
+B.InterpolationFunction(3, rng.standard_normal(20000), [(0.0, 1.0)], [True])
+B.InterpolationFunction(3, rng.standard_normal((20000, 40)), [(0.0, 1.0)] * 2, [False, True])
 tt = B.InterpolationFunctionTemplate(4, (80, 64, 96), [(0.0, 1.0)] * 3, [True, True, True])
 xx = torch.rand((80, 64, 96), dtype=torch.float64, device="cuda")
 tt.sweep_axis(2, xx, [1, 80, 64], [0, 64 * 96, 96], 1)
