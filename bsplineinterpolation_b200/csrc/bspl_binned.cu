@@ -204,15 +204,16 @@ __device__ __forceinline__ int axis_weights_interior(const AxisParams<R>& a, R x
     constexpr int WIN = 2 * O > 0 ? 2 * O : 1;
     R fs;
     const int span = locate_uniform_interior<R, O>(a, x, fs);
-    if (GRAD || k == 0) {
+    if ((GRAD || k == 0) && a.unit_ok) {
         // the span is exact (compared against the reference's knot values); the weights only need
-        // the offset inside the cell
+        // the offset inside the cell (well-conditioned ranges only, see Grid::params)
         const R u = (x - uniform_knot<R>(a, fs)) * a.inv_dx;
         basis_unit<R, O, GRAD>(u, a.inv_dx, w, dw);
     } else {
         R tk[WIN];
         uniform_knot_window<R, O>(a, fs, tk);
-        deriv_weights<R, O>(tk, x, k, w);
+        if (GRAD || k == 0) basis_uniform<R, O, GRAD>(tk, x, a.inv_dx, w, dw);
+        else deriv_weights<R, O>(tk, x, k, w);
     }
     return span - O;
 }

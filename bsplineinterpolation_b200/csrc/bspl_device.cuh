@@ -24,7 +24,7 @@ struct AxisParams {
     int n;           // control points
     int K;           // knots
     int periodic;
-    int pad_;
+    int unit_ok;     // uniform axis whose knots are small multiples of dx: weights may use unit-spaced knots
     long long stride;  // element stride of this axis in the padded coefficient array
 };
 

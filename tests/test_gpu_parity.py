@@ -547,6 +547,33 @@ def test_baseline_cfg3_3d_cubic_256_sample(pkg):
     assert np.abs(fn(nodes) - f[idx[:, 0], idx[:, 1], idx[:, 2]]).max() <= 1e-12 * np.abs(f).max()
 
 
+@pytest.mark.parametrize("offset", [0.0, 10.0, 1000.0, -2.5e5])
+def test_binned_path_on_offset_ranges(pkg, offset):
+    """Ranges far from the origin: the reference divides by differences of rounded knot values
+    (relative error eps * |t| / dx), so the unit-knot weight shortcut of interior tiles is only taken
+    while |t| / dx <= 2^12 (Grid::params); beyond that the knot-based triangle reproduces the
+    reference's rounding.  Value and gradient through the binned path against the oracle, 1e-12."""
+    rng = np.random.default_rng(31)
+    shape = (64, 64, 64)
+    f = smooth_field(shape, rng)
+    lo = [offset, offset - 1.0, offset + 2.0]; hi = [offset + 1.0, offset + 1.0, offset + 2.5]
+    o = OracleSpline(3, shape, [0, 0, 0], lo=lo, hi=hi, f=f, nthreads=8)
+    fn = pkg.InterpolationFunction(3, f, _ranges(lo, hi))
+    pts = np.array(lo) + rng.uniform(0, 1, (1 << 17, 3)) * (np.array(hi) - np.array(lo))
+    assert np.array_equal(fn.locate(pts), o.spans(pts))
+    try:
+        pkg.set_eval_path("binned")
+        vg = fn.value_grad(pts)
+        v = fn(pts)
+    finally:
+        pkg.set_eval_path("auto")
+    _close(v, o.eval(pts, 8))
+    _close(vg[:, 0], o.eval(pts, 8))
+    for k in range(3):
+        dv = [0, 0, 0]; dv[k] = 1
+        _close(vg[:, 1 + k], o.deriv(pts, dv, 8))
+
+
 def test_more_than_2_28_queries_are_sliced(pkg):
     """Maximum sizes: the query sort needs 32 bytes of scratch per query, so batches beyond 2^28
     queries run in slices (bspl_capi.cu: launch_eval).  2^28 + 12 345 device-resident queries; a
