@@ -150,6 +150,9 @@ __global__ void __launch_bounds__(1024) plan_kernel(const uint32_t* __restrict__
 // Sorted query record: coordinates + original index, 4 x sizeof(R) bytes, written and read
 // as whole aligned sectors (the scattered side of the sort is the write, which needs no
 // latency hiding; the evaluation kernel then streams its queries).
+template <typename R> struct Out4;
+template <> struct __align__(32) Out4<double> { double v, g0, g1, g2; };
+template <> struct __align__(16) Out4<float> { float v, g0, g1, g2; };
 template <typename R> struct Rec;
 template <> struct __align__(32) Rec<double> { double x, y, z; unsigned long long idx; };
 template <> struct __align__(16) Rec<float> { float x, y, z; uint32_t idx; };
@@ -341,8 +344,10 @@ __global__ void __launch_bounds__(kEvalThreads, 2)
             }
             R* o = p.out + idx * NOUT;
             if (GRAD) {
-                reinterpret_cast<typename std::conditional<sizeof(R) == 8, double2, float2>::type*>(o)[0] = {v, g0};
-                reinterpret_cast<typename std::conditional<sizeof(R) == 8, double2, float2>::type*>(o)[1] = {g1, g2};
+                // value and gradient leave as one aligned 4-element store (a whole 32-byte sector for fp64)
+                Out4<R> r4;
+                r4.v = v; r4.g0 = g0; r4.g1 = g1; r4.g2 = g2;
+                *reinterpret_cast<Out4<R>*>(o) = r4;
             } else {
                 o[0] = v;
             }

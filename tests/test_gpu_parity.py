@@ -285,6 +285,24 @@ def test_device_pointer_entry_points(pkg):
     _close(vg[:, 2], o.deriv(pts, [0, 1, 0]))
 
 
+def test_unaligned_device_output_takes_the_direct_kernel(pkg):
+    """The binned kernel stores {value, gradient} as one 32-byte vector; an output pointer that is not
+    32-byte aligned must not reach it (launch_eval falls back to the direct kernel)."""
+    import torch
+    rng = np.random.default_rng(12)
+    shape = (32, 32, 32)
+    fn = pkg.InterpolationFunction(3, smooth_field(shape, rng), [(0.0, 1.0)] * 3)
+    q = 1 << 21
+    pts = torch.rand((q, 3), dtype=torch.float64, device="cuda")
+    ref = fn.value_grad(pts)                                   # aligned: binned path
+    buf = torch.empty(q * 4 + 1, dtype=torch.float64, device="cuda")
+    out = buf[1:].view(q, 4)                                   # 8 bytes past a 32-byte boundary
+    assert out.data_ptr() % 32 == 8
+    fn.value_grad(pts, out=out)
+    torch.cuda.synchronize()
+    assert (out - ref).abs().max().item() <= 1e-13 * ref.abs().max().item()
+
+
 def test_empty_and_single_queries(pkg):
     f = np.arange(10.0)
     fn = pkg.InterpolationFunction(3, f, [(0.0, 9.0)])
