@@ -152,7 +152,10 @@ int bspl_evaluate(const bspl_function* fn, int64_t field, const void* pts, int64
 int bspl_evaluate_at(const bspl_function* fn, int64_t field, const void* pts, int64_t q,
                      const int* deriv, void* out, int64_t* first_bad);
 /* Fused value + gradient: out [q][1+dim] = {f, df/dx0, ..., df/dx(dim-1)}; what
- * the reference obtains from one operator() and dim derivative() calls. */
+ * the reference obtains from one operator() and dim derivative() calls.  A device
+ * `out` for a 3-D function should be aligned to 4 elements (32 bytes for fp64):
+ * the tiled kernel writes each result as one vector store; other alignments are
+ * served by the (slower for large batches) direct kernel. */
 int bspl_evaluate_value_grad(const bspl_function* fn, int64_t field, const void* pts, int64_t q,
                              void* out, int on_device, void* stream);
 /* One query set applied to every field (the device analogue of eval_proxy,
