@@ -98,7 +98,7 @@ def test_host_template_construction_matches_oracle(lib_built, order, per):
     both ends of the matrix (compact form, n = 20011)."""
     L = lib_built.lib()
     rng = np.random.default_rng(order * 2 + per)
-    for n in (7, 12, 33, 64, 1500, 4099, 20011):
+    for n in (7, 12, 33, 64, 1500, 4099, 16383, 16384, 20011):
         for nonuni in (0, 1):
             if nonuni and ((order == 0 and not per) or n > 64):
                 continue
