@@ -123,3 +123,29 @@ def test_invalid_arguments_reported(lib_built):
     assert e.value.code == 5  # BSPL_ERR_UNSUPPORTED
     with pytest.raises(BsplError):
         InterpolationFunctionTemplate(3, (8, 8, 8, 8), [(0.0, 1.0)] * 4)
+
+
+def test_host_construction_random_parameters(lib_built):
+    """Property test: for random (order, periodicity, length, range) the host-side knots, range and LU
+    factors are bit-identical to the oracle's -- including ranges far from the origin and tiny or huge
+    spacings, where every rounding of `a + (i - extra/2) * dx` matters."""
+    from hypothesis import given, settings, strategies as st
+
+    L = lib_built.lib()
+
+    @settings(max_examples=80, deadline=None, derandomize=True)
+    @given(order=st.integers(0, 5), per=st.integers(0, 1), n=st.integers(12, 400),
+           lo=st.floats(-1e6, 1e6, allow_nan=False), width=st.floats(1e-6, 1e6, allow_nan=False))
+    def check(order, per, n, lo, width):
+        hi = lo + width
+        if not hi > lo:
+            return
+        o = OracleSpline(order, (n,), [per], lo=[lo], hi=[hi])
+        k, r = _host_knots(L, order, per, n, lo, hi)
+        assert np.array_equal(k, o.knots(0)) and r == o.range(0)
+        P, Lr, U, dg, B, R = _host_factor(L, order, per, n, lo, hi)
+        eL, eU, edg, eB, eR = _row_form_from_oracle(o, n, P, per)
+        for got, exp in ((Lr, eL), (U, eU), (dg, edg), (B, eB), (R, eR)):
+            assert np.array_equal(got, exp)
+
+    check()
