@@ -592,6 +592,32 @@ def test_binned_path_on_offset_ranges(pkg, offset):
         _close(vg[:, 1 + k], o.deriv(pts, dv, 8))
 
 
+def test_span_selection_random_ranges_bit_exact(pkg):
+    """Property test (hypothesis): span - order is exactly the reference's for random orders, lengths,
+    periodicities and ranges (far from the origin, tiny and huge spacings), on adversarial points --
+    on knots, one ulp around them, at the range ends, far outside, several periods away."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None, derandomize=True)
+    @given(order=st.integers(0, 5), per=st.booleans(), n=st.integers(12, 300),
+           lo=st.floats(-1e6, 1e6, allow_nan=False), width=st.floats(1e-6, 1e6, allow_nan=False), seed=st.integers(0, 1 << 30))
+    def check(order, per, n, lo, width, seed):
+        hi = lo + width
+        if not hi > lo:
+            return
+        rng = np.random.default_rng(seed)
+        f = rng.standard_normal(n)
+        o = OracleSpline(order, (n,), [per], lo=[lo], hi=[hi], f=f)
+        fn = pkg.InterpolationFunction(order, f, [(lo, hi)], [per])
+        assert np.array_equal(fn.knots(0), o.knots(0))
+        rlo, rhi = o.range(0)
+        pts = adversarial_points([o.knots(0)], [rlo], [rhi], [per], rng, per_axis=200)
+        assert np.array_equal(fn.locate(pts), o.spans(pts))
+        assert np.array_equal(fn.control_points(), o.control_points())
+
+    check()
+
+
 def test_more_than_2_28_queries_are_sliced(pkg):
     """Maximum sizes: the query sort needs 32 bytes of scratch per query, so batches beyond 2^28
     queries run in slices (bspl_capi.cu: launch_eval).  2^28 + 12 345 device-resident queries; a
