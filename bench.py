@@ -374,7 +374,9 @@ def run_gpu(args):
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                          "kernel_ms": kern_ms, "kernel": "whole evaluate call (key_count, scans, scatter, eval_binned)",
                          "dominant_kernel": dominant, "bytes_per_query": B_QUERY,
-                         "stream_only_frac": q * B_STREAM / (kern_ms * 1e-3) / 1e9 / hbm_peak},
+                         "stream_only_frac": q * B_STREAM / (kern_ms * 1e-3) / 1e9 / hbm_peak,
+                         # measured DRAM bytes (ncu, profiles/traffic.json) over the live step time
+                         "dram_frac": (traffic / (kern_ms * 1e-3) / 1e9 / hbm_peak) if traffic else None},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": qe * 24, "d2h_bytes_per_step": qe * 32,
                     "queries_per_gpu": qe, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err,
