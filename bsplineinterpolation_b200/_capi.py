@@ -42,10 +42,12 @@ SIGNATURES = {
     "bspl_evaluate_value_grad": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp]),
     "bspl_evaluate_fields": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, _vp]),
     "bspl_query_plan_create": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
+    "bspl_template_query_plan_create": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
     "bspl_query_plan_evaluate": (C.c_int, [_vp, _vp, C.c_int64, _ip, C.c_int, _vp, C.c_int, _vp]),
     "bspl_query_plan_destroy": (None, [_vp]),
     "bspl_locate": (C.c_int, [_vp, _vp, C.c_int64, C.POINTER(C.c_int32), C.c_int, _vp]),
     "bspl_band_solve": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64, C.c_int]),
+    "bspl_band_solve_rows": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, _dp, _dp, C.c_int64, C.c_int]),
     "bspl_host_axis_knots": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _dp,
                                        C.c_int64, _i64p, _dp]),
     "bspl_host_axis_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _ip,

@@ -379,6 +379,21 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, int pha
     const long long n_bins = static_cast<long long>(n_tiles) * kBinsPerTile;
     bp.pts = a.pts; bp.q = a.q; bp.n_tiles = n_tiles;
 
+    cudaError_t e = cudaSuccess;
+    if (phases & kBinnedSort) {
+        e = cudaMemsetAsync(sc.counts, 0, sizeof(uint32_t) * n_bins, s);
+        if (e != cudaSuccess) return e;
+        const int grid = kSMs * 4;
+        key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.counts);
+        const int tgrid = (n_tiles * 32 + 255) / 256;
+        tile_totals_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_total);
+        plan_kernel<<<1, 1024, 0, s>>>(sc.tile_total, n_tiles, sc.tile_off, sc.work, sc.n_work, sc.next_item);
+        key_cursor_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_off, sc.cursor);
+        scatter_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.cursor, static_cast<Rec<R>*>(sc.rec));
+        count_launch(5);
+        e = cudaGetLastError();
+        if (e != cudaSuccess || !(phases & kBinnedEval)) return e;
+    }
     // tensor map over the padded coefficient array: dims (z, y, x), row-major
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return cudaErrorNotSupported;
@@ -396,21 +411,6 @@ cudaError_t eval_binned_O(const EvalArgs<R>& a, const BinnedScratch& sc, int pha
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
-    cudaError_t e = cudaSuccess;
-    if (phases & kBinnedSort) {
-        e = cudaMemsetAsync(sc.counts, 0, sizeof(uint32_t) * n_bins, s);
-        if (e != cudaSuccess) return e;
-        const int grid = kSMs * 4;
-        key_count_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.counts);
-        const int tgrid = (n_tiles * 32 + 255) / 256;
-        tile_totals_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_total);
-        plan_kernel<<<1, 1024, 0, s>>>(sc.tile_total, n_tiles, sc.tile_off, sc.work, sc.n_work, sc.next_item);
-        key_cursor_kernel<<<tgrid, 256, 0, s>>>(sc.counts, n_tiles, kBinsPerTile, sc.tile_off, sc.cursor);
-        scatter_kernel<R, O><<<grid, 512, 0, s>>>(bp, sc.cursor, static_cast<Rec<R>*>(sc.rec));
-        count_launch(5);
-        e = cudaGetLastError();
-        if (e != cudaSuccess || !(phases & kBinnedEval)) return e;
-    }
     // the work counter is consumed by every evaluation of a (possibly reused) sorted batch
     e = cudaMemsetAsync(sc.next_item, 0, sizeof(uint32_t), s);
     if (e != cudaSuccess) return e;

@@ -241,7 +241,10 @@ class QueryPlan:
             self.q = pts.shape[0]
             ptr, dev, sp = pts.ctypes.data_as(C.c_void_p), 0, None
         out = C.c_void_p()
-        check(lib().bspl_query_plan_create(fn._h, ptr, self.q, dev, sp, C.byref(out)))
+        # a plan depends on the knots only: a template makes one before any field exists
+        create = (lib().bspl_template_query_plan_create if isinstance(fn, InterpolationFunctionTemplate)
+                  else lib().bspl_query_plan_create)
+        check(create(fn._h, ptr, self.q, dev, sp, C.byref(out)))
         self._h = out
 
     def __call__(self, fn, field=0, derivatives=None, value_grad=False, out=None, device_out=False, stream=None):
@@ -338,6 +341,11 @@ class InterpolationFunctionTemplate:
         check(lib().bspl_template_interpolate(self._h, ptr, n_fields, dev, sp, C.byref(out)))
         return InterpolationFunction(_handle=out)
 
+    def eval_proxy(self, points, stream=None):
+        """InterpolationFunctionTemplate::eval_proxy (InterpolationTemplate.hpp:145-165): the
+        query-dependent work done once, before any field is interpolated; the returned plan
+        evaluates every function this template produces."""
+        return QueryPlan(self, points, stream)
 
     def sweep_axis(self, axis, data, outer_sizes, outer_strides, line_stride, stream=None):
         """In-place banded/cyclic solve of template axis `axis` along every line of a device
@@ -421,6 +429,19 @@ def band_solve(a, rhs, p, q, cyclic, device=0):
     n_rhs = x.size // n
     check(lib().bspl_band_solve(n, p, q, int(bool(cyclic)), a_p, x.ctypes.data_as(C.POINTER(C.c_double)),
                                 n_rhs, device))
+    return x
+
+
+def band_solve_rows(rows, rhs, p, q, cyclic, device=0):
+    """The same solver fed with the band itself: rows[n][p+q+1], rows[i][k] = A(i, i + k - p), column
+    indices wrapping modulo n on a cyclic matrix (bspl_band_solve_rows)."""
+    r_arr, r_p = _f64(rows)
+    x = np.array(rhs, dtype=np.float64, copy=True, order="C")
+    n = r_arr.shape[0]
+    if r_arr.ndim != 2 or r_arr.shape[1] != p + q + 1:
+        raise ValueError("rows must be [n][p+q+1]")
+    check(lib().bspl_band_solve_rows(n, p, q, int(bool(cyclic)), r_p, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                     x.size // n, device))
     return x
 
 

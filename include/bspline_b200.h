@@ -172,6 +172,11 @@ int bspl_evaluate_fields(const bspl_function* fn, const void* pts, int64_t q, vo
 typedef struct bspl_query_plan bspl_query_plan;
 int bspl_query_plan_create(const bspl_function* fn, const void* pts, int64_t q, int on_device,
                            void* stream, bspl_query_plan** out);
+/* InterpolationFunctionTemplate::eval_proxy (InterpolationTemplate.hpp:145-165): the same plan made
+ * from the template alone, before any field has been interpolated -- a plan depends only on the
+ * knots.  It serves every function this template produces. */
+int bspl_template_query_plan_create(const bspl_template* t, const void* pts, int64_t q, int on_device,
+                                    void* stream, bspl_query_plan** out);
 /* value_grad == 0: out[q] (deriv == NULL: values); != 0: out[q][1+dim].  Results are in the
  * order of the original points. */
 int bspl_query_plan_evaluate(const bspl_query_plan* plan, const bspl_function* fn, int64_t field,
@@ -190,6 +195,12 @@ int bspl_locate(const bspl_function* fn, const void* pts, int64_t q, int32_t* ce
  * the device.  Host pointers. */
 int bspl_band_solve(int64_t n, int64_t p, int64_t q, int cyclic, const double* a, double* x,
                     int64_t n_rhs, int device);
+
+/* The same solver fed with the band itself: rows[n][p+q+1], rows[i][k] = A(i, i + k - p); on a
+ * cyclic matrix the column index wraps modulo n (the corner blocks of ExtendedBandMatrix,
+ * BandMatrix.hpp:99-181), otherwise entries outside the matrix are ignored.  O(n (p+q)) memory. */
+int bspl_band_solve_rows(int64_t n, int64_t p, int64_t q, int cyclic, const double* rows, double* x,
+                         int64_t n_rhs, int device);
 
 /* Host-only introspection of template construction (no device needed): the knot
  * vector of one axis exactly as create_knot_vector_ builds it, and the factored

@@ -29,105 +29,10 @@
 #include <vector>
 
 #include "../bspline_b200.h"
+#include "Mesh.hpp"
+#include "util.hpp"
 
 namespace intp {
-
-// ---------------------------------------------------------------- Mesh (host container)
-template <std::size_t D>
-class MeshDimension {
-   public:
-    using size_type = std::size_t;
-    static constexpr size_type dim = D;
-    using index_type = std::array<size_type, D>;
-
-    MeshDimension() : extent_{} {}
-    MeshDimension(index_type extent) : extent_(extent) {}
-    MeshDimension(size_type n) { extent_.fill(n); }
-    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (D > 1)>>
-    MeshDimension(Args... n) : extent_{static_cast<size_type>(n)...} {}
-
-    size_type size() const {
-        return std::accumulate(extent_.begin(), extent_.end(), size_type{1}, std::multiplies<size_type>());
-    }
-    size_type dim_size(size_type d) const { return extent_[d]; }
-    size_type& dim_size(size_type d) { return extent_[d]; }
-    operator index_type() const { return extent_; }
-
-    // row-major, last index fastest
-    size_type indexing(const index_type& idx) const {
-        size_type lin = 0;
-        for (size_type d = 0; d < D; ++d) lin = lin * extent_[d] + idx[d];
-        return lin;
-    }
-    template <typename... Idx>
-    size_type indexing_safe(Idx... idx) const {
-        const index_type a{static_cast<size_type>(idx)...};
-        for (size_type d = 0; d < D; ++d)
-            if (a[d] >= extent_[d]) throw std::runtime_error("Mesh access out of range at dim " + std::to_string(d));
-        return indexing(a);
-    }
-    index_type dimwise_indices(size_type lin) const {
-        index_type idx{};
-        for (size_type d = D; d-- > 0;) { idx[d] = lin % extent_[d]; lin /= extent_[d]; }
-        return idx;
-    }
-    void resize(index_type extent) { extent_ = extent; }
-
-   private:
-    index_type extent_;
-};
-
-template <typename T, std::size_t D, typename Alloc = std::allocator<T>>
-class Mesh {
-   public:
-    using size_type = std::size_t;
-    using val_type = T;
-    static constexpr size_type dim = D;
-    using index_type = typename MeshDimension<D>::index_type;
-    using const_iterator = typename std::vector<T, Alloc>::const_iterator;
-
-    explicit Mesh(const MeshDimension<D>& md) : dims_(md), data_(md.size(), T{}) {}
-    explicit Mesh(size_type n) : Mesh(MeshDimension<D>(n)) {}
-    template <typename... Args, typename = std::enable_if_t<sizeof...(Args) == D && (D > 1) &&
-                                                            (std::is_integral_v<Args> && ...)>>
-    explicit Mesh(Args... n) : Mesh(MeshDimension<D>(static_cast<size_type>(n)...)) {}
-    template <typename It, typename = std::enable_if_t<D == 1 && std::is_convertible_v<
-                               typename std::iterator_traits<It>::iterator_category, std::input_iterator_tag>>>
-    explicit Mesh(std::pair<It, It> range) : dims_(size_type{0}), data_(range.first, range.second) {
-        dims_ = MeshDimension<D>(data_.size());
-    }
-
-    size_type size() const { return data_.size(); }
-    size_type dim_size(size_type d) const { return dims_.dim_size(d); }
-    const MeshDimension<D>& dimension() const { return dims_; }
-    void resize(index_type extent) { dims_.resize(extent); data_.resize(dims_.size()); }
-
-    template <typename... Idx, typename = std::enable_if_t<sizeof...(Idx) == D && (std::is_integral_v<Idx> && ...)>>
-    T& operator()(Idx... i) { return data_[dims_.indexing_safe(i...)]; }
-    template <typename... Idx, typename = std::enable_if_t<sizeof...(Idx) == D && (std::is_integral_v<Idx> && ...)>>
-    const T& operator()(Idx... i) const { return data_[dims_.indexing_safe(i...)]; }
-    T& operator()(index_type i) { return data_[dims_.indexing(i)]; }
-    const T& operator()(index_type i) const { return data_[dims_.indexing(i)]; }
-
-    const T* data() const { return data_.data(); }
-    T* data() { return data_.data(); }
-    const_iterator begin() const { return data_.cbegin(); }
-    const_iterator end() const { return data_.cend(); }
-    index_type iter_indices(const_iterator it) const {
-        return dims_.dimwise_indices(static_cast<size_type>(std::distance(begin(), it)));
-    }
-
-   private:
-    MeshDimension<D> dims_;
-    std::vector<T, Alloc> data_;
-};
-
-namespace util {
-template <typename C>
-auto get_range(C& c) -> std::pair<decltype(c.begin()), decltype(c.end())> {
-    return std::make_pair(c.begin(), c.end());
-}
-}  // namespace util
 
 // ---------------------------------------------------------------- ABI plumbing
 namespace b200_detail {
@@ -226,6 +131,12 @@ class EvalProxy {
     EvalProxy(const bspl_function* fn, const U* points, std::size_t q) : q_(q) {
         bspl_query_plan* p = nullptr;
         b200_detail::check(bspl_query_plan_create(fn, points, static_cast<int64_t>(q), 0, nullptr, &p));
+        plan_.reset(p, b200_detail::PlanDeleter());
+    }
+    // from the template alone, before any field is interpolated (InterpolationTemplate.hpp:145-165)
+    EvalProxy(const bspl_template* tm, const U* points, std::size_t q) : q_(q) {
+        bspl_query_plan* p = nullptr;
+        b200_detail::check(bspl_template_query_plan_create(tm, points, static_cast<int64_t>(q), 0, nullptr, &p));
         plan_.reset(p, b200_detail::PlanDeleter());
     }
     // single point, like the reference's closure: proxy(interp) -> value
@@ -578,6 +489,18 @@ class InterpolationFunctionTemplate {
         b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
         return function_type(b200_detail::FnHandle(f));
     }
+    // eval_proxy (InterpolationTemplate.hpp:145-176): everything that depends on the point only,
+    // done before the fields exist; proxy(function) then evaluates any function of this template.
+    using eval_proxy_t = EvalProxy<T, D, O, U>;
+    eval_proxy_t eval_proxy(DimArray<coord_type> coord) const { return eval_proxy_t(h_.get(), coord.data(), 1); }
+    template <typename... Coords, typename = std::enable_if_t<sizeof...(Coords) == D &&
+                                                              (std::is_arithmetic_v<Coords> && ...)>>
+    eval_proxy_t eval_proxy(Coords... x) const {
+        return eval_proxy(DimArray<coord_type>{static_cast<coord_type>(x)...});
+    }
+    // batched: q points [q][D]
+    eval_proxy_t eval_proxy(const coord_type* points, size_type q) const { return eval_proxy_t(h_.get(), points, q); }
+
     const MeshDim& mesh_dimension() const { return mesh_dimension_; }
     const bspl_template* handle() const { return h_.get(); }
 

@@ -1,0 +1,164 @@
+"""The reference's OWN test programs against this repo's drop-in headers.
+
+`oracle/Makefile reftests` compiles test/src/*.cpp of the reference checkout -- unmodified, where
+they lie -- against include/intp_b200 and links them to libbspline_b200.so; the binaries land in
+oracle/_ref/reftests/ and travel to the GPU box (the sources do not).  Here:
+
+* CPU: every program still compiles and links when the checkout is present; the two that need no
+  device (mesh-test; band-matrix-and-solver-test linked to the CPU stand-in tests/cpp/band_rows_stub.cpp)
+  run and pass; the repo's own band test passes with the stand-in; the device-backed programs fail
+  loudly without a GPU (no CPU fallback).
+* GPU: the regular programs and interpolation-template-test run against the kernels and must exit 0
+  with the reference's own tolerances (1e-14 interpolation-test.cpp:16, 1e-10 band test :30,
+  1e-4 template test :46).  The two speed programs issue millions of single-point calls and are
+  link-checked only.
+
+The file sorts last so that a problem here cannot hide the parity suite behind `-x`.
+"""
+import os
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF = "/root/reference"
+RT = os.path.join(ROOT, "oracle", "_ref", "reftests")
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+INC = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "intp_b200")]
+ALL = ["mesh-test", "band-matrix-and-solver-test", "bspline-test", "interpolation-test",
+       "interpolation-template-test", "interpolation-speed-test", "interpolation-eval-proxy-test"]
+
+have_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "test", "src")),
+                              reason="reference checkout not present (GPU box)")
+
+
+@have_ref
+def test_reference_programs_compile_and_link_unmodified(lib_built):
+    subprocess.check_call(["make", "-s", "-j4", "-f", os.path.join(ROOT, "oracle", "Makefile"), "reftests", "REF=" + REF],
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for name in ALL:
+        assert os.access(os.path.join(RT, name), os.X_OK), name
+
+
+@have_ref
+def test_reference_mesh_test_passes(lib_built):
+    test_reference_programs_compile_and_link_unmodified(lib_built)
+    r = subprocess.run([os.path.join(RT, "mesh-test")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _with_stub(tmp_path, source, std):
+    exe = tmp_path / "band_cpu"
+    subprocess.check_call([CXX, "-std=" + std, "-O1", "-Wall"] + INC + [source,
+                          os.path.join(ROOT, "tests", "cpp", "band_rows_stub.cpp"), "-o", str(exe)],
+                          stderr=subprocess.DEVNULL)
+    return subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+
+
+def test_band_headers_with_cpu_stand_in(tmp_path):
+    """Host containers + the row form handed to bspl_band_solve_rows, no device involved."""
+    r = _with_stub(tmp_path, os.path.join(ROOT, "tests", "cpp", "band_dropin_test.cpp"), "c++17")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all band solver checks passed" in r.stdout
+
+
+@have_ref
+def test_reference_band_test_with_cpu_stand_in(tmp_path):
+    r = _with_stub(tmp_path, os.path.join(REF, "test", "src", "band-matrix-and-solver-test.cpp"), "c++20")
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_device_backed_program_fails_loudly_without_gpu(tmp_path, lib_built):
+    """No CPU fallback behind the headers: without a device the library reports BSPL_ERR_CUDA and
+    the header throws."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = tmp_path / "band_gpu"
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    subprocess.check_call([CXX, "-std=c++17", "-O1"] + INC + [os.path.join(ROOT, "tests", "cpp", "band_dropin_test.cpp"),
+                          "-o", str(exe), "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode != 0
+    assert "CUDA" in r.stderr or "cuda" in r.stderr
+
+
+@pytest.mark.gpu
+def test_band_headers_on_the_gpu(tmp_path, lib_built):
+    exe = tmp_path / "band_gpu"
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    subprocess.check_call([CXX, "-std=c++17", "-O1"] + INC + [os.path.join(ROOT, "tests", "cpp", "band_dropin_test.cpp"),
+                          "-o", str(exe), "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mesh-test", "band-matrix-and-solver-test", "interpolation-test",
+                                  "interpolation-template-test"])
+def test_reference_program_passes_on_the_gpu(name):
+    exe = os.path.join(RT, name)
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/reftests/%s was not prebuilt (needs the reference checkout at build time)" % name)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["direct", "binned"])
+def test_template_level_eval_proxy(lib_built, path):
+    """InterpolationFunctionTemplate::eval_proxy (InterpolationTemplate.hpp:145-165): the plan is made
+    from the template alone, before any field exists, and serves every function interpolated later."""
+    import numpy as np
+    pkg = lib_built
+    rng = np.random.default_rng(29)
+    shape = (33, 40, 37)
+    per = [False, True, False]
+    ranges = [(0.0, 1.0), (-1.0, 1.0), (2.0, 3.0)]
+    pts = np.array([0.0, -1.0, 2.0]) + rng.uniform(0, 1, (30000, 3)) * np.array([1.0, 2.0, 1.0])
+    try:
+        pkg.set_eval_path(path)
+        t = pkg.InterpolationFunctionTemplate(3, shape, ranges, per)
+        plan = t.eval_proxy(pts)  # no function yet
+        fa = t.interpolate(rng.standard_normal(shape))
+        fb = t.interpolate(rng.standard_normal((2,) + shape))
+        assert np.array_equal(plan(fa), fa.evaluate(pts))
+        assert np.array_equal(plan(fb, field=1, value_grad=True), fb.value_grad(pts, field=1))
+        assert np.array_equal(plan(fa, derivatives=[0, 2, 1]), fa.derivative(pts, [0, 2, 1]))
+        other = pkg.InterpolationFunctionTemplate(3, shape, ranges, per).interpolate(rng.standard_normal(shape))
+        with pytest.raises(pkg.BsplError):
+            plan(other)  # a function of another template
+    finally:
+        pkg.set_eval_path("auto")
+
+
+@pytest.mark.gpu
+def test_band_solve_rows_equals_dense_entry(lib_built):
+    """bspl_band_solve_rows (band rows, wrapped columns) against bspl_band_solve (dense input) and
+    the oracle's restatement of BandLU: bit-identical solutions."""
+    import numpy as np
+    from oracle.pyoracle import port_band_solve
+    pkg = lib_built
+    rng = np.random.default_rng(31)
+    for n, p, q, cyc in [(64, 1, 1, False), (50, 2, 3, False), (64, 2, 2, True), (41, 1, 3, True), (37, 3, 1, True)]:
+        w = p + q + 1
+        rows = rng.uniform(-0.2, 0.2, (n, w))
+        rows[:, p] = 1.0 + rng.uniform(0, 1, n)  # diagonally dominant: no pivoting needed
+        a = np.zeros((n, n))
+        for i in range(n):
+            for k in range(w):
+                j = i + k - p
+                if 0 <= j < n:
+                    a[i, j] = rows[i, k]
+                elif cyc:
+                    a[i, j % n] = rows[i, k]
+        rhs = rng.standard_normal((3, n))
+        x_rows = pkg.band_solve_rows(rows, rhs, p, q, cyc)
+        x_dense = pkg.band_solve(a, rhs, p, q, cyc)
+        assert np.array_equal(x_rows, x_dense)
+        for r in range(3):
+            assert np.array_equal(x_rows[r], port_band_solve(a, rhs[r], p, q, cyc))
+            assert np.abs(a @ x_rows[r] - rhs[r]).max() < 1e-12
