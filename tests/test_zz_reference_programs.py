@@ -9,8 +9,8 @@ oracle/_ref/reftests/ and travel to the GPU box (the sources do not).  Here:
   run and pass; the repo's own band test passes with the stand-in; the device-backed programs fail
   loudly without a GPU (no CPU fallback).
 * GPU: the regular programs and interpolation-template-test run against the kernels and must exit 0
-  with the reference's own tolerances (1e-14 interpolation-test.cpp:16, 1e-10 band test :30,
-  1e-4 template test :46).  The two speed programs issue millions of single-point calls and are
+  with the reference's own tolerances (1e-15 bspline-test.cpp:45, 1e-14 interpolation-test.cpp:16,
+  1e-10 band test :30, 1e-4 template test :46); profiles/r1_reference_programs.txt keeps a B200 run.  The two speed programs issue millions of single-point calls and are
   link-checked only.
 
 The file sorts last so that a problem here cannot hide the parity suite behind `-x`.
@@ -96,7 +96,7 @@ def test_band_headers_on_the_gpu(tmp_path, lib_built):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["mesh-test", "band-matrix-and-solver-test", "interpolation-test",
+@pytest.mark.parametrize("name", ["mesh-test", "band-matrix-and-solver-test", "bspline-test", "interpolation-test",
                                   "interpolation-template-test"])
 def test_reference_program_passes_on_the_gpu(name):
     exe = os.path.join(RT, name)
