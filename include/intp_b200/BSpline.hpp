@@ -10,6 +10,7 @@
 
 #include <array>
 #include <cstdint>
+#include <iostream>
 #include <memory>
 #include <new>
 #include <stdexcept>
@@ -65,6 +66,13 @@ class BSpline {
     template <typename... InputIters, typename = std::enable_if_t<sizeof...(InputIters) == D>>
     BSpline(ControlPointContainer ctrl_pts, std::pair<InputIters, InputIters>... knot_iter_pairs)
         : BSpline(DimArray<bool>{}, std::move(ctrl_pts), knot_iter_pairs...) {}
+
+    // A view of an existing device spline (what InterpolationFunction::spline() returns): the host
+    // copies of knots and control points describe it, evaluation goes to the shared device storage.
+    BSpline(DimArray<bool> periodicity, ControlPointContainer ctrl_pts, DimArray<KnotContainer> knots,
+            DimArray<std::pair<knot_type, knot_type>> ranges, std::shared_ptr<bspl_function> device_spline)
+        : periodicity_(periodicity), knots_(std::move(knots)), ctrl_(std::move(ctrl_pts)), range_(ranges),
+          device_(std::move(device_spline)) {}
 
     // BSpline.hpp:217-242
     void load_knots(size_type d, KnotContainer knots) {
@@ -152,6 +160,20 @@ class BSpline {
     bool periodicity(size_type d) const { return periodicity_[d]; }
     constexpr size_type get_order() const { return order; }
     void set_device(int ordinal) { device_ordinal_ = ordinal; device_.reset(); }
+    // control points, one row of the last axis per line (BSpline.hpp:611-628, there under INTP_DEBUG)
+    void debug_output(std::ostream& os = std::cout) const {
+        os << "\n[DEBUG] Control Points (raw data):\n";
+        const auto prec = os.precision(17);
+        const size_type row = ctrl_.dim_size(D - 1);
+        size_type idx = 0;
+        for (auto v : ctrl_) {
+            if (idx % row == 0) os << "[DEBUG] ";
+            os << v << ' ';
+            if (++idx % row == 0) os << '\n';
+        }
+        os << '\n';
+        os.precision(prec);
+    }
     // the device-resident spline (built on first use)
     const bspl_function* handle() const { return device(); }
 

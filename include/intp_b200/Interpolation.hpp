@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "../bspline_b200.h"
+#include "BSpline.hpp"
 #include "Mesh.hpp"
 #include "util.hpp"
 
@@ -83,7 +84,9 @@ void merge_component(const U* field, std::size_t m, std::size_t k, T* data) {
 struct FnDeleter { void operator()(bspl_function* p) const { bspl_function_destroy(p); } };
 struct PlanDeleter { void operator()(bspl_query_plan* p) const { bspl_query_plan_destroy(p); } };
 struct TmDeleter { void operator()(bspl_template* p) const { bspl_template_destroy(p); } };
-using FnHandle = std::unique_ptr<bspl_function, FnDeleter>;
+// shared only with the BSpline view returned by spline(); copies of a function clone the device storage
+using FnHandle = std::shared_ptr<bspl_function>;
+inline FnHandle own(bspl_function* p) { return FnHandle(p, FnDeleter()); }
 using TmHandle = std::unique_ptr<bspl_template, TmDeleter>;
 
 // One axis of a template: a (min, max) pair of numbers -> uniform; a pair of iterators
@@ -223,8 +226,9 @@ class InterpolationFunction {
             if (o.h_) {
                 bspl_function* p = nullptr;
                 b200_detail::check(bspl_function_clone(o.h_.get(), &p));
-                h_.reset(p);
+                h_ = b200_detail::own(p);
             }
+            spline_view_.reset();
             cache_info();
         }
         return *this;
@@ -341,6 +345,21 @@ class InterpolationFunction {
         return std::vector<coord_type>(k.begin(), k.end());
     }
     const bspl_function* handle() const { return h_.get(); }
+    // spline() (Interpolation.hpp:265): the underlying B-spline -- knots, plain control points and the
+    // BSpline evaluation interface -- as a view sharing this function's device storage (scalar T).
+    // The reference is valid until this function is assigned to or re-interpolated.
+    using spline_type = BSpline<T, D, O, U>;
+    template <typename S = spline_type>
+    const S& spline() const {
+        static_assert(components == 1, "spline(): scalar functions only");
+        if (!spline_view_) {
+            DimArray<std::vector<coord_type>> kn;
+            for (size_type d = 0; d < D; ++d) kn[d] = knots(d);
+            auto sp = std::make_shared<S>(periodic_, control_points(), std::move(kn), range_, h_);
+            spline_view_ = sp;
+        }
+        return *static_cast<const S*>(spline_view_.get());
+    }
 
    private:
     explicit InterpolationFunction(b200_detail::FnHandle h) : h_(std::move(h)) { cache_info(); }
@@ -394,6 +413,7 @@ class InterpolationFunction {
     }
 
     b200_detail::FnHandle h_;
+    mutable std::shared_ptr<const void> spline_view_;  // BSpline<T,D,O,U>, built by spline() on demand
     DimArray<bool> periodic_{};
     DimArray<bool> uniform_{};
     DimArray<size_type> n_{};
@@ -462,7 +482,7 @@ class InterpolationFunctionTemplate {
             const std::vector<U> fields = b200_detail::split_components<T, U>(f_mesh.data(), f_mesh.size());
             b200_detail::check(bspl_template_interpolate(h_.get(), fields.data(), static_cast<int64_t>(K), 0, nullptr, &f));
         }
-        return function_type(b200_detail::FnHandle(f));
+        return function_type(b200_detail::own(f));
     }
     template <typename It, size_type DD = D, typename = std::enable_if_t<DD == 1>>
     function_type interpolate(std::pair<It, It> f_range) const {
@@ -480,6 +500,7 @@ class InterpolationFunctionTemplate {
             b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), fields.data(),
                                                               static_cast<int64_t>(K), 0, nullptr));
         }
+        interp.spline_view_.reset();
         interp.cache_info();
     }
     // device-resident mesh (row-major, same shape), enqueued on `stream`
@@ -487,7 +508,7 @@ class InterpolationFunctionTemplate {
         static_assert(b200_detail::components_of<T, U>::value == 1, "device meshes: scalar T (pass K fields through the C ABI)");
         bspl_function* f = nullptr;
         b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
-        return function_type(b200_detail::FnHandle(f));
+        return function_type(b200_detail::own(f));
     }
     // eval_proxy (InterpolationTemplate.hpp:145-176): everything that depends on the point only,
     // done before the fields exist; proxy(function) then evaluates any function of this template.

@@ -122,6 +122,38 @@ int main() {
             same = same && pv[i] == other(coords_3d[3 * i], coords_3d[3 * i + 1], coords_3d[3 * i + 2]);
         expect(same, "eval_proxy (batched)");
     }
+    {   // template-level eval_proxy (InterpolationTemplate.hpp:145-165): made before any field exists
+        std::array<double, 3> c{coords_3d[3], coords_3d[4], coords_3d[5]};
+        decltype(tmpl)::eval_proxy_t early = tmpl.eval_proxy(c);
+        auto early2 = tmpl.eval_proxy(c[0], c[1], c[2]);
+        auto later = tmpl.interpolate(f3d);
+        expect(early(later) == later(c) && early2(interp3) == interp3(c), "template eval_proxy before interpolate");
+    }
+    {   // spline(): a BSpline view on the function's own device storage
+        const auto& sp = interp3.spline();
+        std::array<double, 3> c{coords_3d[0], coords_3d[1], coords_3d[2]};
+        bool ok = sp(c) == interp3(c) && sp.periodicity(0) == interp3.periodicity(0) && sp.get_order() == 3 &&
+                  sp.range(2) == interp3.range(2) && sp.knots_num(1) == 6 + 4;
+        ok = ok && sp.derivative_at({std::make_pair(c[0], std::size_t{1}), std::make_pair(c[1], std::size_t{0}),
+                                     std::make_pair(c[2], std::size_t{3})}) == interp3.derivative(c, 1, 0, 3);
+        const auto ctrl = interp3.control_points();
+        ok = ok && sp.control_points().size() == 210 && sp.control_points()(1, 2, 3) == ctrl(1, 2, 3);
+        // the same spline rebuilt from its knots and control points (BSpline.hpp:188-210)
+        BSpline<double, 3, 3> rebuilt(sp.control_points(), std::make_pair(sp.knots_begin(0), sp.knots_end(0)),
+                                      std::make_pair(sp.knots_begin(1), sp.knots_end(1)),
+                                      std::make_pair(sp.knots_begin(2), sp.knots_end(2)));
+        ok = ok && std::abs(rebuilt(c) - sp(c)) <= 1e-14 * std::abs(sp(c));  // generic-knot vs uniform-axis kernels
+        auto ev = rebuilt.pre_calc_coef({std::make_pair(c[0], std::size_t{3}), std::make_pair(c[1], std::size_t{3}),
+                                         std::make_pair(c[2], std::size_t{3})});
+        ok = ok && ev(rebuilt) == rebuilt(c);
+        expect(ok, "spline() view, BSpline from knots, pre_calc_coef");
+    }
+    {   // Mesh line iterators (Mesh.hpp:342-371) feeding a 1-D interpolation: column 2 of f2-like data
+        Mesh<double, 2> m2{5, 5};
+        for (std::size_t i = 0; i < 25; ++i) m2(m2.dimension().dimwise_indices(i)) = std::sin(0.3 * double(i));
+        InterpolationFunction<double, 1, 3> col(std::make_pair(m2.begin(0, {0, 2}), m2.end(0, {0, 2})), std::make_pair(0., 4.));
+        expect(std::abs(col(3.) - m2(3, 2)) < 1e-14, "1-D interpolation over a Mesh line iterator");
+    }
     InterpolationFunction<double, 3, 3> into;
     tmpl.interpolate(into, f3d);
     expect(into(1., 2., 3.) == interp3(1., 2., 3.), "interpolate(function&, mesh)");
