@@ -162,3 +162,32 @@ def test_band_solve_rows_equals_dense_entry(lib_built):
         for r in range(3):
             assert np.array_equal(x_rows[r], port_band_solve(a, rhs[r], p, q, cyc))
             assert np.abs(a @ x_rows[r] - rhs[r]).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_tiny_host_calls_equal_batched_results(lib_built):
+    """Host-pointer calls of at most a page (the reference's one-point operator()) go through mapped
+    pinned memory instead of the copy pipeline; the numbers must be those of a large batch."""
+    import numpy as np
+    pkg = lib_built
+    rng = np.random.default_rng(37)
+    shape = (21, 26, 19)
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0), (-2.0, 2.0), (5.0, 6.0)], [True, False, False])
+    fn = t.interpolate(rng.standard_normal((2,) + shape))
+    pts = np.array([0.0, -2.0, 5.0]) + rng.uniform(0, 1, (3000, 3)) * np.array([1.0, 4.0, 1.0])
+    big_v = fn.evaluate(pts, field=1)
+    big_g = fn.value_grad(pts, field=0)
+    big_d = fn.derivative(pts, [1, 0, 2], field=1)
+    big_f = fn.evaluate_fields(pts)
+    for q in (1, 2, 31, 128):
+        assert np.array_equal(fn.evaluate(pts[:q], field=1), big_v[:q])
+        assert np.array_equal(fn.value_grad(pts[:q], field=0), big_g[:q])
+        assert np.array_equal(fn.derivative(pts[:q], [1, 0, 2], field=1), big_d[:q])
+        assert np.array_equal(fn.evaluate_fields(pts[:q]), big_f[:, :q])
+        plan = fn.eval_proxy(pts[:q])
+        assert np.array_equal(plan(fn, field=1), big_v[:q])
+        assert np.array_equal(plan(fn, field=0, value_grad=True), big_g[:q])
+    # 1-D and float take the same route
+    f1 = pkg.InterpolationFunction(5, rng.standard_normal(40), [(0.0, 1.0)], [True], dtype=np.float32)
+    x = rng.uniform(0, 1, 2000).astype(np.float32)
+    assert np.array_equal(f1.evaluate(x[:9]), f1.evaluate(x)[:9])
