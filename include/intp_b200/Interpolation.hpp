@@ -5,10 +5,13 @@
 //   InterpolationFunction{,1D}        <- src/include/Interpolation.hpp:17-540
 //   InterpolationFunctionTemplate{,1D}<- src/include/InterpolationTemplate.hpp:32-604
 // but every number is produced on the GPU through the C ABI of bspline_b200.h (link
-// libbspline_b200.so).  Semantics kept from the reference build used as oracle
-// (INTP_PERIODIC_NO_DUMMY_POINT): a periodic axis with N samples has period N*dx and its
-// closing sample is implicit.  Added: batched evaluate()/value_grad() on host or device
-// pointers and a batched interpolate() for many fields.
+// libbspline_b200.so).  INTP_PERIODIC_NO_DUMMY_POINT keeps its meaning (reference README.md:57):
+// defined, a periodic axis with N samples has period N*dx and its closing sample is implicit;
+// undefined (the reference's default), the last sample of a periodic axis is the dummy copy of the
+// first one and is dropped (InterpolationTemplate.hpp:255-265, :464-487).  The other reference
+// macros (INTP_CELL_LAYOUT, INTP_MULTITHREAD, allocators) describe CPU layout / threading and have
+// no effect here.  Added: batched evaluate()/value_grad() on host or device pointers and a batched
+// interpolate() for many fields.
 //
 // Requires C++17.  T must equal U and be double or float.
 #ifndef INTP_B200_INTERPOLATION_HPP
@@ -108,6 +111,23 @@ AxisSpec make_axis(const std::pair<X, X>& r) {
         a.hi = a.coords.back();
     }
     return a;
+}
+
+#ifdef INTP_PERIODIC_NO_DUMMY_POINT
+constexpr bool kDummyPoint = false;
+#else
+constexpr bool kDummyPoint = true;
+#endif
+
+// Drop the closing (dummy) sample of every periodic axis: [N0]..[N_{D-1}] -> [N_d - periodic_d].
+template <typename T, std::size_t D>
+std::vector<T> strip_dummy(const T* data, const MeshDimension<D>& full, const std::array<bool, D>& periodic) {
+    typename MeshDimension<D>::index_type ext{};
+    for (std::size_t d = 0; d < D; ++d) ext[d] = full.dim_size(d) - (periodic[d] ? 1 : 0);
+    const MeshDimension<D> kept(ext);
+    std::vector<T> out(kept.size());
+    for (std::size_t i = 0; i < out.size(); ++i) out[i] = data[full.indexing(kept.dimwise_indices(i))];
+    return out;
 }
 
 inline int& default_device() {
@@ -437,19 +457,24 @@ class InterpolationFunctionTemplate {
     // (periodicity, mesh dimension, ranges...)  InterpolationTemplate.hpp:60-79
     template <typename... Ts, typename = std::enable_if_t<sizeof...(Ts) == D>>
     InterpolationFunctionTemplate(DimArray<bool> periodicity, MeshDim mesh_dimension, std::pair<Ts, Ts>... x_ranges)
-        : mesh_dimension_(mesh_dimension) {
+        : mesh_dimension_(mesh_dimension), periodicity_(periodicity) {
         const std::array<b200_detail::AxisSpec, D> ax{b200_detail::make_axis(x_ranges)...};
         int64_t n[D];
         int per[D];
         double lo[D], hi[D];
         const double* coords[D];
         for (size_type d = 0; d < D; ++d) {
-            n[d] = static_cast<int64_t>(mesh_dimension.dim_size(d));
+            // data points the library solves for: the dummy sample of a periodic axis is not one of them
+            const size_type dummy = (b200_detail::kDummyPoint && periodicity[d]) ? 1 : 0;
+            if (mesh_dimension.dim_size(d) <= dummy) throw std::runtime_error("empty axis at dimension " + std::to_string(d));
+            n[d] = static_cast<int64_t>(mesh_dimension.dim_size(d) - dummy);
             per[d] = periodicity[d] ? 1 : 0;
             lo[d] = ax[d].lo;
             hi[d] = ax[d].hi;
             coords[d] = ax[d].coords.empty() ? nullptr : ax[d].coords.data();
-            if (coords[d] && ax[d].coords.size() != mesh_dimension.dim_size(d) + (periodicity[d] ? 1 : 0))
+            // abscissae: one per sample, plus the period's end when that sample is implicit
+            // (Interpolation.hpp:379-391)
+            if (coords[d] && ax[d].coords.size() != static_cast<size_type>(n[d]) + (periodicity[d] ? 1 : 0))
                 throw std::runtime_error("Inconsistency between knot number and interpolated value number at dimension " +
                                          std::to_string(d));
         }
@@ -476,10 +501,13 @@ class InterpolationFunctionTemplate {
         check_mesh(f_mesh);
         bspl_function* f = nullptr;
         constexpr size_type K = b200_detail::components_of<T, U>::value;
+        std::vector<T> kept;
+        const T* data = samples(f_mesh, kept);
+        [[maybe_unused]] const size_type m = kept.empty() ? f_mesh.size() : kept.size();
         if constexpr (K == 1) {
-            b200_detail::check(bspl_template_interpolate(h_.get(), f_mesh.data(), 1, 0, nullptr, &f));
+            b200_detail::check(bspl_template_interpolate(h_.get(), data, 1, 0, nullptr, &f));
         } else {  // K fields, one per component
-            const std::vector<U> fields = b200_detail::split_components<T, U>(f_mesh.data(), f_mesh.size());
+            const std::vector<U> fields = b200_detail::split_components<T, U>(data, m);
             b200_detail::check(bspl_template_interpolate(h_.get(), fields.data(), static_cast<int64_t>(K), 0, nullptr, &f));
         }
         return function_type(b200_detail::own(f));
@@ -493,17 +521,21 @@ class InterpolationFunctionTemplate {
         check_mesh(f_mesh);
         if (!interp.h_) { interp = interpolate(f_mesh); return; }
         constexpr size_type K = b200_detail::components_of<T, U>::value;
+        std::vector<T> kept;
+        const T* data = samples(f_mesh, kept);
+        [[maybe_unused]] const size_type m = kept.empty() ? f_mesh.size() : kept.size();
         if constexpr (K == 1) {
-            b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), f_mesh.data(), 1, 0, nullptr));
+            b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), data, 1, 0, nullptr));
         } else {
-            const std::vector<U> fields = b200_detail::split_components<T, U>(f_mesh.data(), f_mesh.size());
+            const std::vector<U> fields = b200_detail::split_components<T, U>(data, m);
             b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), fields.data(),
                                                               static_cast<int64_t>(K), 0, nullptr));
         }
         interp.spline_view_.reset();
         interp.cache_info();
     }
-    // device-resident mesh (row-major, same shape), enqueued on `stream`
+    // device-resident mesh, row-major, enqueued on `stream`.  Its shape is that of the data points:
+    // a device mesh never carries the dummy sample of a periodic axis.
     function_type interpolate_device(const T* d_mesh, void* stream = nullptr) const {
         static_assert(b200_detail::components_of<T, U>::value == 1, "device meshes: scalar T (pass K fields through the C ABI)");
         bspl_function* f = nullptr;
@@ -530,7 +562,20 @@ class InterpolationFunctionTemplate {
         for (size_type d = 0; d < D; ++d)
             if (m.dim_size(d) != mesh_dimension_.dim_size(d)) throw std::runtime_error("mesh shape differs from the template's");
     }
+    // the samples handed to the library: the mesh itself, or (dummy-point mode, periodic axes) a copy
+    // without the closing sample of every periodic axis, kept alive in `kept`
+    const T* samples(const Mesh<T, D>& f_mesh, std::vector<T>& kept) const {
+        if constexpr (b200_detail::kDummyPoint) {
+            for (size_type d = 0; d < D; ++d)
+                if (periodicity_[d]) {
+                    kept = b200_detail::strip_dummy<T, D>(f_mesh.data(), mesh_dimension_, periodicity_);
+                    return kept.data();
+                }
+        }
+        return f_mesh.data();
+    }
     MeshDim mesh_dimension_;
+    DimArray<bool> periodicity_{};
     b200_detail::TmHandle h_;
 };
 
@@ -540,11 +585,13 @@ class InterpolationFunction1D : public InterpolationFunction<T, 1, O, U> {
     using base = InterpolationFunction<T, 1, O, U>;
 
    public:
-    // default x range [0, N-1], or [0, N] when periodic  Interpolation.hpp:518-533
+    // default x range [0, N-1]; [0, N] for a periodic axis whose closing sample is implicit
+    // (INTP_PERIODIC_NO_DUMMY_POINT)  Interpolation.hpp:518-533
     template <typename It>
     InterpolationFunction1D(std::pair<It, It> f_range, bool periodicity = false)
         : InterpolationFunction1D(
-              std::make_pair(U{}, static_cast<U>(std::distance(f_range.first, f_range.second) - (periodicity ? 0 : 1))),
+              std::make_pair(U{}, static_cast<U>(std::distance(f_range.first, f_range.second) -
+                                                 ((periodicity && !b200_detail::kDummyPoint) ? 0 : 1))),
               f_range, periodicity) {}
     template <typename C1, typename C2, typename It>
     InterpolationFunction1D(std::pair<C1, C2> x_range, std::pair<It, It> f_range, bool periodicity = false)

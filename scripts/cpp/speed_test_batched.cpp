@@ -6,6 +6,7 @@
 // including every host<->device copy.  Prints the table of BASELINE.md section 2.1.
 //
 // Build and run: scripts/run_reftests.sh
+#define INTP_PERIODIC_NO_DUMMY_POINT  // the reference's own test configuration (test/CMakeLists.txt:46)
 #include <intp_b200/Interpolation.hpp>
 
 #include <algorithm>

@@ -2,6 +2,7 @@
 // test/src/interpolation-test.cpp, written against the same class names, with the
 // Mathematica golden vectors supplied through golden_vectors.inc (generated from
 // tests/golden/reference_vectors.json by tests/test_cpp_dropin.py).  Needs a GPU.
+#define INTP_PERIODIC_NO_DUMMY_POINT  // the reference's own test configuration (test/CMakeLists.txt:46)
 #include <intp_b200/Interpolation.hpp>
 
 #include <cmath>

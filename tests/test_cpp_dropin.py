@@ -29,6 +29,28 @@ def _build(tmp_path, lib_built):
     return exe
 
 
+def _build_plain(tmp_path, source, lib_built):
+    exe = tmp_path / os.path.splitext(source)[0]
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    subprocess.check_call([CXX, "-std=c++17", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", source), "-o", str(exe),
+                           "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg])
+    return exe
+
+
+def test_dummy_point_convention_compiles(tmp_path, lib_built):
+    """The reference's default periodic convention (INTP_PERIODIC_NO_DUMMY_POINT undefined)."""
+    assert os.path.exists(_build_plain(tmp_path, "dummy_point_test.cpp", lib_built))
+
+
+@pytest.mark.gpu
+def test_dummy_point_convention_on_the_gpu(tmp_path, lib_built):
+    exe = _build_plain(tmp_path, "dummy_point_test.cpp", lib_built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
 def test_header_compiles_and_links(tmp_path, lib_built):
     assert os.path.exists(_build(tmp_path, lib_built))
 

@@ -10,7 +10,9 @@ oracle/_ref/reftests/ and travel to the GPU box (the sources do not).  Here:
   loudly without a GPU (no CPU fallback).
 * GPU: the regular programs and interpolation-template-test run against the kernels and must exit 0
   with the reference's own tolerances (1e-15 bspline-test.cpp:45, 1e-14 interpolation-test.cpp:16,
-  1e-10 band test :30, 1e-4 template test :46); profiles/r1_reference_programs.txt keeps a B200 run.  The two speed programs issue millions of single-point calls and are
+  1e-10 band test :30, 1e-4 template test :46); profiles/r1_reference_programs.txt keeps a B200 run.
+  interpolation-test is built twice: with INTP_PERIODIC_NO_DUMMY_POINT (the reference's test
+  configuration) and without it (the reference's default periodic convention, "dummy-point").  The two speed programs issue millions of single-point calls and are
   link-checked only.
 
 The file sorts last so that a problem here cannot hide the parity suite behind `-x`.
@@ -26,7 +28,7 @@ REF = "/root/reference"
 RT = os.path.join(ROOT, "oracle", "_ref", "reftests")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 INC = ["-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "include", "intp_b200")]
-ALL = ["mesh-test", "band-matrix-and-solver-test", "bspline-test", "interpolation-test",
+ALL = ["mesh-test", "band-matrix-and-solver-test", "bspline-test", "interpolation-test", "interpolation-test.dummy-point",
        "interpolation-template-test", "interpolation-speed-test", "interpolation-eval-proxy-test"]
 
 have_ref = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "test", "src")),
@@ -105,6 +107,44 @@ def test_reference_program_passes_on_the_gpu(name):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+# interpolation-test.cpp without INTP_PERIODIC_NO_DUMMY_POINT declares its periodic "segment" function
+# with order 1 instead of 0 (:325) and compares it with piecewise-constant values, so that one case fails
+# for the reference itself (rel. error 0.353278); its CI only builds with the macro.  A faithful
+# drop-in shows the same picture: 19 cases succeed, that one fails with the same error.
+DUMMY_EXPECTED_FAILURE = "1D test (segment) with periodic boundary"
+
+
+def _dummy_point_outcome(stdout):
+    ok = [ln for ln in stdout.splitlines() if ln.rstrip().endswith("succeed") or "succeed." in ln]
+    bad = [ln for ln in stdout.splitlines() if "failed" in ln]
+    return len(ok), bad
+
+
+@have_ref
+def test_reference_itself_in_dummy_point_mode(tmp_path):
+    """Pins the expectation above on the UNMODIFIED reference (its own headers, CPU)."""
+    exe = tmp_path / "ref_dummy"
+    subprocess.check_call([CXX, "-std=c++20", "-O1", "-DINTP_CELL_LAYOUT", "-I", os.path.join(REF, "src", "include"),
+                           os.path.join(REF, "test", "src", "interpolation-test.cpp"), "-o", str(exe)],
+                          stderr=subprocess.DEVNULL)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    n_ok, bad = _dummy_point_outcome(r.stdout)
+    assert r.returncode == 1 and n_ok == 19 and len(bad) == 1 and DUMMY_EXPECTED_FAILURE in bad[0], r.stdout[-3000:]
+    assert "Relative Error = 0.353278" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_interpolation_test_dummy_point_mode_on_the_gpu():
+    exe = os.path.join(RT, "interpolation-test.dummy-point")
+    if not os.access(exe, os.X_OK):
+        pytest.skip("oracle/_ref/reftests/interpolation-test.dummy-point was not prebuilt")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    print(r.stdout[-4000:])
+    n_ok, bad = _dummy_point_outcome(r.stdout)
+    assert n_ok == 19 and len(bad) == 1 and DUMMY_EXPECTED_FAILURE in bad[0], r.stdout[-4000:] + r.stderr[-2000:]
+    assert "Relative Error = 0.353278" in r.stdout  # the reference's own figure for its mis-declared case
 
 
 @pytest.mark.gpu
