@@ -11,7 +11,15 @@ namespace bspl {
 namespace {
 
 constexpr int kFieldThreads = 512;
-constexpr int kQPerThread = 4;
+constexpr int kSMs = 148;       // B200
+// Queries per thread: their 2 * (O+1) weights stay in registers for the whole sweep over the fields, so
+// the count follows an 80-register budget (cubic fp64: 5; ptxas: 128 registers, no spills).
+template <typename R, int O>
+constexpr int queries_per_thread() {
+    constexpr int per_query = 2 * (O + 1) * static_cast<int>(sizeof(R)) / 4;
+    constexpr int k = 80 / per_query;
+    return k > 6 ? 6 : (k < 2 ? 2 : k);
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -26,12 +34,13 @@ struct FieldsParams {
     const R* pts;
     R* out;
     long long q;
+    int per_cta;  // queries per CTA (a multiple of 32): CTA b owns [b * per_cta, (b + 1) * per_cta)
     int deriv[2];
 };
 
 template <typename R, int O>
 __global__ void __launch_bounds__(kFieldThreads, 1) eval_fields_smem_kernel(const FieldsParams<R> p) {
-    constexpr int W = O + 1, K = kQPerThread;
+    constexpr int W = O + 1, K = queries_per_thread<R, O>();
     constexpr int WIN = 2 * O > 0 ? 2 * O : 1;
     extern __shared__ __align__(128) unsigned char fields_raw[];
     R* fld = reinterpret_cast<R*>(fields_raw);
@@ -44,7 +53,9 @@ __global__ void __launch_bounds__(kFieldThreads, 1) eval_fields_smem_kernel(cons
     __syncthreads();
 
     // this thread's queries: q0 + k * kFieldThreads, so that a warp's stores are contiguous
-    const long long q0 = static_cast<long long>(blockIdx.x) * (kFieldThreads * K) + tid;
+    const long long q_begin = static_cast<long long>(blockIdx.x) * p.per_cta;
+    const long long q_end = q_begin + p.per_cta < p.q ? q_begin + p.per_cta : p.q;
+    const long long q0 = q_begin + tid;
     R w0[K][W], w1[K][W];
     int off[K];
 #pragma unroll
@@ -53,7 +64,7 @@ __global__ void __launch_bounds__(kFieldThreads, 1) eval_fields_smem_kernel(cons
         off[k] = 0;
 #pragma unroll
         for (int i = 0; i < W; ++i) { w0[k][i] = R(0); w1[k][i] = R(0); }
-        if (q < p.q) {
+        if (q < q_end) {
 #pragma unroll
             for (int d = 0; d < 2; ++d) {
                 R x = p.pts[q * 2 + d];
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(kFieldThreads, 1) eval_fields_smem_kernel(cons
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             const long long q = q0 + static_cast<long long>(k) * kFieldThreads;
-            if (q < p.q) {
+            if (q < q_end) {
                 const R* c = fld + off[k];
                 R v = R(0);
 #pragma unroll
@@ -121,8 +132,16 @@ cudaError_t fields_O(const EvalArgs<R>& a, cudaStream_t s) {
     auto k = eval_fields_smem_kernel<R, O>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    const long long per_cta = static_cast<long long>(kFieldThreads) * kQPerThread;
-    const long long grid = (a.q + per_cta - 1) / per_cta;
+    // One CTA per SM at a time (the field fills shared memory), every CTA sweeps all fields: the batch is
+    // cut into a whole number of waves of equal CTAs instead of full CTAs plus a ragged last wave
+    // (2^20 queries: 444 CTAs of 2 368 queries in 3 waves, not 512 of 2 048 in 3.46).
+    const long long cap = static_cast<long long>(kFieldThreads) * queries_per_thread<R, O>();
+    const long long waves = (a.q + cap * kSMs - 1) / (cap * kSMs);
+    long long grid = waves * kSMs;
+    long long per_cta = ((a.q + grid - 1) / grid + 31) / 32 * 32;
+    if (per_cta > cap) per_cta = cap / 32 * 32;
+    grid = (a.q + per_cta - 1) / per_cta;
+    p.per_cta = static_cast<int>(per_cta);
     k<<<static_cast<unsigned>(grid), kFieldThreads, smem, s>>>(p);
     count_launch();
     return cudaGetLastError();
