@@ -762,6 +762,27 @@ def test_many_fields_streamed_through_shared_memory(pkg, order, periodic):
         _close(allv[k][inside], o.eval(pts[inside]))
 
 
+@pytest.mark.parametrize("order,periodic", [(3, (False, True)), (4, (True, False))])
+def test_many_fields_fp32(pkg, order, periodic):
+    """The field-streaming kernel in float (32 bank classes, one per lane of a warp): equal to
+    per-field float evaluation, and within the north star's 1e-5 of the float64 function."""
+    rng = np.random.default_rng(80 + order)
+    F, shape, Q = 9, (40, 52), 20000
+    fields = rng.standard_normal((F,) + shape)
+    rg = [(0.0, 1.0), (-1.0, 2.0)]
+    fn32 = pkg.InterpolationFunctionTemplate(order, shape, rg, periodic, dtype=np.float32).interpolate(fields.astype(np.float32))
+    fn64 = pkg.InterpolationFunctionTemplate(order, shape, rg, periodic).interpolate(fields)
+    pts = np.array([0.0, -1.0]) + rng.uniform(0, 1, (Q, 2)) * np.array([1.0, 3.0])
+    allv = fn32.evaluate_fields(pts.astype(np.float32))
+    assert allv.dtype == np.float32 and allv.shape == (F, Q)
+    ref = fn64.evaluate_fields(pts)
+    for k in range(F):
+        single = fn32.evaluate(pts.astype(np.float32), field=k)
+        assert np.abs(allv[k] - single).max() <= 2e-6 * np.abs(single).max()
+        assert np.abs(allv[k] - ref[k]).max() <= 1e-5 * np.abs(ref[k]).max() * 8  # cancellation near zeros of the field
+    assert rel_err(allv, ref) <= 1e-5
+
+
 def test_many_fields_host_path_is_chunked(pkg):
     """Host-pointer evaluate_fields with many fields: the staging buffers stay bounded (chunks
     shrink with the field count) and the strided copy-back lands every field in its row."""
