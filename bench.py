@@ -203,6 +203,81 @@ def bind_to_gpu_numa_node(local):
     return None
 
 
+# ----------------------------------------------------------------------------- other configurations
+def other_configs(B, torch, dev, hbm_peak):
+    """BASELINE.json configs 0, 1 and 4 (cfg1, cfg2, cfg5 in SURVEY 8), device resident, CUDA events,
+    median of 5 after 2 warm-up calls; algorithmic bytes per SURVEY 8(d)."""
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.median(ts))
+
+    def device_field(shape):
+        return torch.from_numpy(smooth_field_np(shape)).to(dev)
+
+    res = {}
+    # cfg1: 2-D cubic 1024^2, value+gradient (the mesh is L2 resident: direct gather kernel)
+    try:
+        shape, Q = (1024, 1024), 1 << 24
+        fn = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 2, device=dev.index).interpolate(device_field(shape))
+        pts = torch.rand((Q, 2), dtype=torch.float64, device=dev)
+        out = torch.empty((Q, 3), dtype=torch.float64, device=dev)
+        ms = timed(lambda: fn.value_grad(pts, out=out))
+        bq = 8 * 2 + 8 * 3 + 8 * 16
+        res["cfg1_2d_cubic_1024"] = {"queries": Q, "outputs": "value+gradient", "ms": ms, "Mpts_per_s": Q / ms / 1e3,
+                                      "bytes_per_query": bq, "roofline_frac": Q * bq / ms / 1e6 / hbm_peak}
+        del fn, pts, out
+    except Exception as exc:
+        res["cfg1_2d_cubic_1024"] = {"error": str(exc)}
+    torch.cuda.empty_cache()
+    # cfg2: 1-D order-5 periodic, 2^24 mesh points, value + first derivative; solve time beside it
+    try:
+        shape, Q = (1 << 24,), 1 << 24
+        t0 = time.perf_counter()
+        t = B.InterpolationFunctionTemplate(5, shape, [(0.0, 1.0)], [True], device=dev.index)
+        template_ms = 1e3 * (time.perf_counter() - t0)
+        f = device_field(shape)
+        fn = t.interpolate(f)
+        solve_ms = timed(lambda: t.interpolate(f, into=fn), warm=1)
+        pts = torch.rand((Q, 1), dtype=torch.float64, device=dev)
+        out = torch.empty((Q, 2), dtype=torch.float64, device=dev)
+        ms = timed(lambda: fn.value_grad(pts, out=out))
+        bq = 8 + 8 * 2 + 8 * 6
+        res["cfg2_1d_quintic_periodic_2e24"] = {"queries": Q, "outputs": "value+d1", "ms": ms, "Mpts_per_s": Q / ms / 1e3,
+                                                 "bytes_per_query": bq, "roofline_frac": Q * bq / ms / 1e6 / hbm_peak,
+                                                 "solve_ms": solve_ms, "template_host_ms": template_ms}
+        del fn, pts, out, f, t
+    except Exception as exc:
+        res["cfg2_1d_quintic_periodic_2e24"] = {"error": str(exc)}
+    torch.cuda.empty_cache()
+    # cfg5: 4 096 fields on one 128^2 cubic mesh: batched solve, then one query set on every field
+    try:
+        F, shape, Q = 4096, (128, 128), 1 << 20
+        t = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 2, device=dev.index)
+        f = torch.rand((F,) + shape, dtype=torch.float64, device=dev)
+        fn = t.interpolate(f)
+        solve_ms = timed(lambda: t.interpolate(f, into=fn), warm=1)
+        pts = torch.rand((Q, 2), dtype=torch.float64, device=dev)
+        out = torch.empty((F, Q), dtype=torch.float64, device=dev)
+        ms = timed(lambda: fn.evaluate_fields(pts, out=out), reps=3, warm=1)
+        sbytes = 2 * 8 * 2 * float(F * shape[0] * shape[1])
+        res["cfg5_4096_fields_128x128"] = {"fields": F, "queries": Q, "solve_ms": solve_ms,
+                                            "solve_roofline_frac": sbytes / solve_ms / 1e6 / hbm_peak,
+                                            "evaluate_fields_ms": ms, "G_evaluations_per_s": F * Q / ms / 1e6,
+                                            "output_stream_frac": F * Q * 8 / ms / 1e6 / hbm_peak}
+        del fn, pts, out, f, t
+    except Exception as exc:
+        res["cfg5_4096_fields_128x128"] = {"error": str(exc)}
+    torch.cuda.empty_cache()
+    return res
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def run_gpu(args):
     import torch
@@ -353,6 +428,12 @@ def run_gpu(args):
         cpu = {"value": CPU_SAMPLE / dt / 1e6, "unit": "Mpts/s", "cores": threads, "kind": ref.kind,
                "sample": ref.describe(dt)}
 
+    # ---- the other BASELINE configurations, device resident (one GPU only; each guarded: a failure
+    # is recorded, it cannot take the headline numbers above with it)
+    other = None
+    if world == 1 and not args.no_other:
+        other = other_configs(B, torch, dev, hbm_peak)
+
     if rank == 0:
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -384,6 +465,7 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "solve": solve,
+            "other_configs": other,
             "checksum": checksum,
         }
         emit(line)
@@ -402,6 +484,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the cfg1 / cfg2 / cfg5 timings")
     args = ap.parse_args()
     # stdout carries the one JSON line and nothing else: whatever libraries print while the run is
     # in progress (NCCL's version banner, compiler chatter of the CPU checker) goes to stderr
