@@ -58,6 +58,16 @@ def _with_stub(tmp_path, source, std):
     return subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
 
 
+def test_mesh_header(tmp_path):
+    """Mesh.hpp is pure host code: its own checks run here (the reference's mesh-test covers it too,
+    where the checkout is present)."""
+    exe = tmp_path / "mesh_own"
+    subprocess.check_call([CXX, "-std=c++17", "-O1", "-Wall", "-Werror"] + INC +
+                          [os.path.join(ROOT, "tests", "cpp", "mesh_dropin_test.cpp"), "-o", str(exe)])
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "all mesh checks passed" in r.stdout, r.stdout + r.stderr
+
+
 def test_band_headers_with_cpu_stand_in(tmp_path):
     """Host containers + the row form handed to bspl_band_solve_rows, no device involved."""
     r = _with_stub(tmp_path, os.path.join(ROOT, "tests", "cpp", "band_dropin_test.cpp"), "c++17")
