@@ -1,0 +1,3 @@
+// The reference installs its headers as <BSplineInterpolation/BSpline.hpp> (CMakeLists.txt:38-40); this
+// forwarder keeps that include line working with -I<repo>/include.
+#include "../intp_b200/BSpline.hpp"

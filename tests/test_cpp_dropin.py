@@ -61,3 +61,30 @@ def test_reference_scenarios_through_cpp_header(tmp_path, lib_built):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+def _cmake_consumer(tmp_path, lib_built):
+    """The reference README's CMake snippet (find_package + target_link_libraries) and include line
+    (<BSplineInterpolation/Interpolation.hpp>), unchanged, against cmake/BSplineInterpolationConfig.cmake."""
+    import shutil
+    cmake = shutil.which("cmake")
+    if cmake is None:
+        pytest.skip("cmake not available")
+    build = tmp_path / "consumer_build"
+    subprocess.check_call([cmake, "-S", os.path.join(ROOT, "tests", "cmake_consumer"), "-B", str(build),
+                           "-DBSplineInterpolation_DIR=" + os.path.join(ROOT, "cmake"), "-DCMAKE_CXX_COMPILER=" + CXX],
+                          stdout=subprocess.DEVNULL)
+    subprocess.check_call([cmake, "--build", str(build)], stdout=subprocess.DEVNULL)
+    return build / "main"
+
+
+def test_cmake_package_builds_reference_style_project(tmp_path, lib_built):
+    assert os.path.exists(_cmake_consumer(tmp_path, lib_built))
+
+
+@pytest.mark.gpu
+def test_cmake_package_project_runs_on_the_gpu(tmp_path, lib_built):
+    exe = _cmake_consumer(tmp_path, lib_built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
