@@ -80,11 +80,3 @@ def _cmake_consumer(tmp_path, lib_built):
 
 def test_cmake_package_builds_reference_style_project(tmp_path, lib_built):
     assert os.path.exists(_cmake_consumer(tmp_path, lib_built))
-
-
-@pytest.mark.gpu
-def test_cmake_package_project_runs_on_the_gpu(tmp_path, lib_built):
-    exe = _cmake_consumer(tmp_path, lib_built)
-    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
-    print(r.stdout)
-    assert r.returncode == 0, r.stdout + r.stderr

@@ -241,3 +241,13 @@ def test_tiny_host_calls_equal_batched_results(lib_built):
     f1 = pkg.InterpolationFunction(5, rng.standard_normal(40), [(0.0, 1.0)], [True], dtype=np.float32)
     x = rng.uniform(0, 1, 2000).astype(np.float32)
     assert np.array_equal(f1.evaluate(x[:9]), f1.evaluate(x)[:9])
+
+
+@pytest.mark.gpu
+def test_cmake_package_project_runs_on_the_gpu(tmp_path, lib_built):
+    """tests/cmake_consumer: the reference README's project, built through cmake/BSplineInterpolationConfig.cmake."""
+    from test_cpp_dropin import _cmake_consumer
+    exe = _cmake_consumer(tmp_path, lib_built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
