@@ -441,6 +441,48 @@ class InterpolationFunction {
     DimArray<std::pair<coord_type, coord_type>> range_{};
 };
 
+// ---------------------------------------------------------------- many fields on one mesh (new)
+// What InterpolationFunctionTemplate::interpolate_fields returns: F scalar fields interpolated on the
+// template's mesh in one batched solve, held as ONE device object, so that a query set is located
+// once and applied to every field (the reference's template + eval_proxy use case,
+// InterpolationTemplate.hpp:118-176, as one call).
+template <typename T, std::size_t D, std::size_t O, typename U = double>
+class InterpolationFieldSet {
+    static_assert(std::is_same_v<T, U>, "field sets hold scalar fields of the coordinate type");
+
+   public:
+    using size_type = std::size_t;
+    InterpolationFieldSet() = default;
+    size_type size() const { return n_fields_; }
+    // out[q] = field k at points[q][D]
+    void evaluate(size_type k, const U* points, size_type q, T* out) const {
+        b200_detail::check(bspl_evaluate(need(), static_cast<int64_t>(k), points, static_cast<int64_t>(q), nullptr, out, 0, nullptr));
+    }
+    // out[size()][q]: every field at the same points (host pointers)
+    void evaluate_all(const U* points, size_type q, T* out) const {
+        b200_detail::check(bspl_evaluate_fields(need(), points, static_cast<int64_t>(q), out, 0, nullptr));
+    }
+    // the same on device pointers, enqueued on `stream`
+    void evaluate_all_device(const U* d_points, size_type q, T* d_out, void* stream = nullptr) const {
+        b200_detail::check(bspl_evaluate_fields(need(), d_points, static_cast<int64_t>(q), d_out, 1, stream));
+    }
+    // out[q][1 + D] = value and gradient of field k
+    void evaluate_value_grad(size_type k, const U* points, size_type q, T* out) const {
+        b200_detail::check(bspl_evaluate_value_grad(need(), static_cast<int64_t>(k), points, static_cast<int64_t>(q), out, 0, nullptr));
+    }
+    const bspl_function* handle() const { return h_.get(); }
+
+   private:
+    friend class InterpolationFunctionTemplate<T, D, O, U>;
+    InterpolationFieldSet(b200_detail::FnHandle h, size_type n) : h_(std::move(h)), n_fields_(n) {}
+    const bspl_function* need() const {
+        if (!h_) throw std::runtime_error("empty InterpolationFieldSet");
+        return h_.get();
+    }
+    b200_detail::FnHandle h_;
+    size_type n_fields_ = 0;
+};
+
 // ---------------------------------------------------------------- InterpolationFunctionTemplate
 template <typename T, std::size_t D, std::size_t O, typename U = double>
 class InterpolationFunctionTemplate {
@@ -541,6 +583,19 @@ class InterpolationFunctionTemplate {
         bspl_function* f = nullptr;
         b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
         return function_type(b200_detail::own(f));
+    }
+    // batched interpolate (new): n_fields meshes of this template's data shape stored back to back,
+    // [n_fields][n0]...[n_{D-1}] (no dummy samples), solved in one pass per axis
+    InterpolationFieldSet<T, D, O, U> interpolate_fields(const T* fields, size_type n_fields) const {
+        bspl_function* f = nullptr;
+        b200_detail::check(bspl_template_interpolate(h_.get(), fields, static_cast<int64_t>(n_fields), 0, nullptr, &f));
+        return InterpolationFieldSet<T, D, O, U>(b200_detail::own(f), n_fields);
+    }
+    InterpolationFieldSet<T, D, O, U> interpolate_fields_device(const T* d_fields, size_type n_fields,
+                                                                void* stream = nullptr) const {
+        bspl_function* f = nullptr;
+        b200_detail::check(bspl_template_interpolate(h_.get(), d_fields, static_cast<int64_t>(n_fields), 1, stream, &f));
+        return InterpolationFieldSet<T, D, O, U>(b200_detail::own(f), n_fields);
     }
     // eval_proxy (InterpolationTemplate.hpp:145-176): everything that depends on the point only,
     // done before the fields exist; proxy(function) then evaluates any function of this template.
