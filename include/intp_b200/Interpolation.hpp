@@ -13,7 +13,8 @@
 // no effect here.  Added: batched evaluate()/value_grad() on host or device pointers and a batched
 // interpolate() for many fields.
 //
-// Requires C++17.  T must equal U and be double or float.
+// Requires C++17.  U (coordinates, arithmetic) is double or float; T is U, another arithmetic type
+// (converted), or a trivially copyable aggregate of U values (carried as fields).
 #ifndef INTP_B200_INTERPOLATION_HPP
 #define INTP_B200_INTERPOLATION_HPP
 
@@ -56,32 +57,57 @@ template <typename T> constexpr bspl_dtype dtype_of() {
     return std::is_same_v<T, double> ? BSPL_F64 : BSPL_F32;
 }
 
-// Vector-valued T (e.g. the reference's Vec<2, float> circle, interpolation-test.cpp:674-703): any
-// trivially copyable aggregate of K values of the coordinate type U is carried as K fields of one
-// function -- K independent scalar splines sharing knots, factors and query work.
+// How a value type T travels on a library whose arithmetic runs in the coordinate type U:
+//  - T == U: directly;
+//  - another arithmetic T (the reference's InterpolationFunction<float, D, O> on double coordinates):
+//    one field, converted on the way in and out -- the arithmetic is U's, only the storage was T's;
+//  - vector-valued T (e.g. the reference's Vec<2, float> circle, interpolation-test.cpp:674-703): any
+//    trivially copyable aggregate of K values of U is carried as K fields of one function -- K
+//    independent scalar splines sharing knots, factors and query work.
 template <typename T, typename U>
 struct components_of {
-    static_assert(std::is_arithmetic_v<T> ? std::is_same_v<T, U>
-                                          : (std::is_trivially_copyable_v<T> && sizeof(T) % sizeof(U) == 0),
-                  "T must be the coordinate type U or a trivially copyable aggregate of U values");
-    static constexpr std::size_t value = sizeof(T) / sizeof(U);
+    static_assert(std::is_arithmetic_v<T> || (std::is_trivially_copyable_v<T> && sizeof(T) % sizeof(U) == 0),
+                  "T must be arithmetic or a trivially copyable aggregate of values of the coordinate type U");
+    static constexpr std::size_t value = std::is_arithmetic_v<T> ? 1 : sizeof(T) / sizeof(U);
 };
+// T is handed to the library as it is
+template <typename T, typename U>
+constexpr bool direct_v = std::is_same_v<T, U>;
 // [m][K] interleaved -> [K][m]
 template <typename T, typename U>
 std::vector<U> split_components(const T* data, std::size_t m) {
     constexpr std::size_t K = components_of<T, U>::value;
     std::vector<U> out(K * m);
-    const U* in = reinterpret_cast<const U*>(data);
-    for (std::size_t i = 0; i < m; ++i)
-        for (std::size_t k = 0; k < K; ++k) out[k * m + i] = in[i * K + k];
+    if constexpr (std::is_arithmetic_v<T>) {
+        for (std::size_t i = 0; i < m; ++i) out[i] = static_cast<U>(data[i]);
+    } else {
+        const U* in = reinterpret_cast<const U*>(data);
+        for (std::size_t i = 0; i < m; ++i)
+            for (std::size_t k = 0; k < K; ++k) out[k * m + i] = in[i * K + k];
+    }
     return out;
 }
-// [m] values of component k -> slot k of [m][stride / K ...] interleaved storage
+// [m] values of component k -> slot k of [m][K] interleaved storage
 template <typename T, typename U>
 void merge_component(const U* field, std::size_t m, std::size_t k, T* data) {
     constexpr std::size_t K = components_of<T, U>::value;
-    U* out = reinterpret_cast<U*>(data);
-    for (std::size_t i = 0; i < m; ++i) out[i * K + k] = field[i];
+    if constexpr (std::is_arithmetic_v<T>) {
+        for (std::size_t i = 0; i < m; ++i) data[i] = static_cast<T>(field[i]);
+    } else {
+        U* out = reinterpret_cast<U*>(data);
+        for (std::size_t i = 0; i < m; ++i) out[i * K + k] = field[i];
+    }
+}
+// one value from its K components
+template <typename T, typename U>
+T from_components(const U* c) {
+    if constexpr (std::is_arithmetic_v<T>) {
+        return static_cast<T>(c[0]);
+    } else {
+        T v;
+        std::memcpy(&v, c, sizeof(T));
+        return v;
+    }
 }
 
 struct FnDeleter { void operator()(bspl_function* p) const { bspl_function_destroy(p); } };
@@ -169,14 +195,12 @@ class EvalProxy {
         for (std::size_t k = 0; k < K; ++k)
             b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), static_cast<int64_t>(k), nullptr, 0,
                                                         &buf[k], 0, nullptr));
-        T v;
-        std::memcpy(&v, buf, sizeof(T));
-        return v;
+        return b200_detail::from_components<T, U>(buf);
     }
     // batched: out[q]
     void operator()(const function_type& interp, T* out) const {
         constexpr std::size_t K = b200_detail::components_of<T, U>::value;
-        if constexpr (K == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 0, out, 0, nullptr));
         } else {
             std::vector<U> tmp(q_);
@@ -188,7 +212,7 @@ class EvalProxy {
         }
     }
     void value_grad(const function_type& interp, T* out) const {
-        static_assert(b200_detail::components_of<T, U>::value == 1, "value_grad: scalar functions only");
+        static_assert(b200_detail::direct_v<T, U>, "value_grad: T must be the coordinate type");
         b200_detail::check(bspl_query_plan_evaluate(plan_.get(), interp.handle(), 0, nullptr, 1, out, 0, nullptr));
     }
     std::size_t size() const { return q_; }
@@ -308,7 +332,7 @@ class InterpolationFunction {
     }
     // out[q][1 + D] = value, d/dx0, ..., d/dx(D-1)
     void evaluate_value_grad(const coord_type* points, size_type q, val_type* out) const {
-        if constexpr (components == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_evaluate_value_grad(need(), 0, points, static_cast<int64_t>(q), out, 0, nullptr));
         } else {
             std::vector<coord_type> tmp(q * (1 + D));
@@ -321,12 +345,12 @@ class InterpolationFunction {
     }
     // device pointers: scalar functions; for vector-valued T evaluate field k with the C ABI (handle())
     void evaluate_device(const coord_type* d_points, size_type q, val_type* d_out, void* stream = nullptr) const {
-        static_assert(components == 1, "device-pointer evaluation: scalar functions only");
+        static_assert(b200_detail::direct_v<T, U>, "device-pointer evaluation: T must be the coordinate type");
         b200_detail::check(bspl_evaluate(need(), 0, d_points, static_cast<int64_t>(q), nullptr, d_out, 1, stream));
     }
     void evaluate_value_grad_device(const coord_type* d_points, size_type q, val_type* d_out,
                                     void* stream = nullptr) const {
-        static_assert(components == 1, "device-pointer evaluation: scalar functions only");
+        static_assert(b200_detail::direct_v<T, U>, "device-pointer evaluation: T must be the coordinate type");
         b200_detail::check(bspl_evaluate_value_grad(need(), 0, d_points, static_cast<int64_t>(q), d_out, 1, stream));
     }
 
@@ -348,7 +372,7 @@ class InterpolationFunction {
         typename MeshDimension<D>::index_type ext{};
         for (size_type d = 0; d < D; ++d) ext[d] = n_[d];
         Mesh<T, D> m{MeshDimension<D>(ext)};
-        if constexpr (components == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_function_control_points(need(), 0, m.data()));
         } else {
             std::vector<coord_type> tmp(m.size());
@@ -371,7 +395,7 @@ class InterpolationFunction {
     using spline_type = BSpline<T, D, O, U>;
     template <typename S = spline_type>
     const S& spline() const {
-        static_assert(components == 1, "spline(): scalar functions only");
+        static_assert(b200_detail::direct_v<T, U>, "spline(): T must be the coordinate type");
         if (!spline_view_) {
             DimArray<std::vector<coord_type>> kn;
             for (size_type d = 0; d < D; ++d) kn[d] = knots(d);
@@ -396,12 +420,10 @@ class InterpolationFunction {
             else
                 b200_detail::check(bspl_evaluate(need(), static_cast<int64_t>(k), c, 1, dv, &buf[k], 0, nullptr));
         }
-        val_type v;
-        std::memcpy(&v, buf, sizeof(val_type));
-        return v;
+        return b200_detail::from_components<T, U>(buf);
     }
     void many(const coord_type* points, size_type q, const int* dv, val_type* out) const {
-        if constexpr (components == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_evaluate(need(), 0, points, static_cast<int64_t>(q), dv, out, 0, nullptr));
         } else {
             std::vector<coord_type> tmp(q);
@@ -546,7 +568,7 @@ class InterpolationFunctionTemplate {
         std::vector<T> kept;
         const T* data = samples(f_mesh, kept);
         [[maybe_unused]] const size_type m = kept.empty() ? f_mesh.size() : kept.size();
-        if constexpr (K == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_template_interpolate(h_.get(), data, 1, 0, nullptr, &f));
         } else {  // K fields, one per component
             const std::vector<U> fields = b200_detail::split_components<T, U>(data, m);
@@ -566,7 +588,7 @@ class InterpolationFunctionTemplate {
         std::vector<T> kept;
         const T* data = samples(f_mesh, kept);
         [[maybe_unused]] const size_type m = kept.empty() ? f_mesh.size() : kept.size();
-        if constexpr (K == 1) {
+        if constexpr (b200_detail::direct_v<T, U>) {
             b200_detail::check(bspl_template_interpolate_into(h_.get(), interp.h_.get(), data, 1, 0, nullptr));
         } else {
             const std::vector<U> fields = b200_detail::split_components<T, U>(data, m);
@@ -579,7 +601,7 @@ class InterpolationFunctionTemplate {
     // device-resident mesh, row-major, enqueued on `stream`.  Its shape is that of the data points:
     // a device mesh never carries the dummy sample of a periodic axis.
     function_type interpolate_device(const T* d_mesh, void* stream = nullptr) const {
-        static_assert(b200_detail::components_of<T, U>::value == 1, "device meshes: scalar T (pass K fields through the C ABI)");
+        static_assert(b200_detail::direct_v<T, U>, "device meshes: T must be the coordinate type (pass K fields through the C ABI)");
         bspl_function* f = nullptr;
         b200_detail::check(bspl_template_interpolate(h_.get(), d_mesh, 1, 1, stream, &f));
         return function_type(b200_detail::own(f));

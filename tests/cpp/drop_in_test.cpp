@@ -155,26 +155,6 @@ int main() {
         InterpolationFunction<double, 1, 3> col(std::make_pair(m2.begin(0, {0, 2}), m2.end(0, {0, 2})), std::make_pair(0., 4.));
         expect(std::abs(col(3.) - m2(3, 2)) < 1e-14, "1-D interpolation over a Mesh line iterator");
     }
-    {   // batched interpolate + one query set on every field
-        constexpr std::size_t F = 9;
-        std::vector<double> fields(F * 210);
-        for (std::size_t k = 0; k < F; ++k)
-            for (std::size_t i = 0; i < 210; ++i) fields[k * 210 + i] = f3[i] * double(k + 1) - double(k);
-        auto set = tmpl.interpolate_fields(fields.data(), F);
-        const std::size_t q = vals_3d.size();
-        std::vector<double> all(F * q), one(q);
-        set.evaluate_all(coords_3d.data(), q, all.data());
-        bool ok = set.size() == F;
-        for (std::size_t k : {std::size_t{0}, std::size_t{4}, F - 1}) {
-            set.evaluate(k, coords_3d.data(), q, one.data());
-            for (std::size_t i = 0; i < q; ++i) {
-                ok = ok && std::abs(all[k * q + i] - one[i]) <= 1e-14 * (1. + std::abs(one[i]));
-                // field k = (k+1) f3 - k: the spline is linear in the data
-                ok = ok && std::abs(one[i] - (vals_3d[i] * double(k + 1) - double(k))) < 1e-13 * double(k + 1);
-            }
-        }
-        expect(ok, "interpolate_fields + evaluate_all");
-    }
     InterpolationFunction<double, 3, 3> into;
     tmpl.interpolate(into, f3d);
     expect(into(1., 2., 3.) == interp3(1., 2., 3.), "interpolate(function&, mesh)");

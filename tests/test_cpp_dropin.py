@@ -12,7 +12,7 @@ from conftest import ROOT
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
-def _build(tmp_path, lib_built):
+def _build(tmp_path, lib_built, source="drop_in_test.cpp"):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["interpolation"]
     inc = tmp_path / "golden_vectors.inc"
     with open(inc, "w") as fh:
@@ -20,10 +20,10 @@ def _build(tmp_path, lib_built):
         for k, v in g.items():
             fh.write("const std::vector<double> %s = {%s};\n" % (k, ", ".join(repr(float(x)) for x in v)))
         fh.write("}\n")
-    exe = tmp_path / "drop_in_test"
+    exe = tmp_path / os.path.splitext(source)[0]
     pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
     cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", str(tmp_path),
-           os.path.join(ROOT, "tests", "cpp", "drop_in_test.cpp"), "-o", str(exe),
+           os.path.join(ROOT, "tests", "cpp", source), "-o", str(exe),
            "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg]
     subprocess.check_call(cmd)
     return exe
@@ -53,6 +53,7 @@ def test_dummy_point_convention_on_the_gpu(tmp_path, lib_built):
 
 def test_header_compiles_and_links(tmp_path, lib_built):
     assert os.path.exists(_build(tmp_path, lib_built))
+    assert os.path.exists(_build(tmp_path, lib_built, "drop_in_test2.cpp"))
 
 
 @pytest.mark.gpu

@@ -251,3 +251,13 @@ def test_cmake_package_project_runs_on_the_gpu(tmp_path, lib_built):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     print(r.stdout)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_header_additions_on_the_gpu(tmp_path, lib_built):
+    """tests/cpp/drop_in_test2.cpp: InterpolationFieldSet (batched interpolate) and T != U value types."""
+    from test_cpp_dropin import _build
+    exe = _build(tmp_path, lib_built, "drop_in_test2.cpp")
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
+    print(r.stdout[-4000:])
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
