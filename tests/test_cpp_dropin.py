@@ -38,6 +38,13 @@ def _build_plain(tmp_path, source, lib_built):
     return exe
 
 
+def test_host_helpers_of_the_header(tmp_path, lib_built):
+    """Dummy-sample stripping and value-type conversion: pure host code, runs here."""
+    exe = _build_plain(tmp_path, "host_helpers_test.cpp", lib_built)
+    r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0 and "all host helper checks passed" in r.stdout, r.stdout + r.stderr
+
+
 def test_dummy_point_convention_compiles(tmp_path, lib_built):
     """The reference's default periodic convention (INTP_PERIODIC_NO_DUMMY_POINT undefined)."""
     assert os.path.exists(_build_plain(tmp_path, "dummy_point_test.cpp", lib_built))
