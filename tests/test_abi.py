@@ -31,6 +31,21 @@ def test_header_symbols_exported(lib_built):
     assert b"sm_100a" in L.bspl_version()
 
 
+def test_header_is_plain_c(tmp_path, lib_built):
+    """include/bspline_b200.h is a C header (C99, -pedantic): what cgo / JNI / ctypes-style bindings need."""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text("#include <bspline_b200.h>\n"
+                   "int main(void) { bspl_template* t = 0; bspl_function* f = 0; bspl_query_plan* p = 0;\n"
+                   "  (void)t; (void)f; (void)p; return bspl_version() == 0 || BSPL_OK != 0; }\n")
+    exe = tmp_path / "c_abi"
+    pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-std=c99", "-pedantic", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-o", str(exe), "-L", pkg, "-lbspline_b200", "-Wl,-rpath," + pkg])
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
 def test_no_cpu_fallback_in_product():
     """The product package must not import or link the oracle."""
     pkg = os.path.join(ROOT, "bsplineinterpolation_b200")
