@@ -414,6 +414,24 @@ def run_gpu(args):
         sbytes = 2 * 8 * 3 * float(np.prod(SOLVE_MESH))
         solve = {"mesh": list(SOLVE_MESH), "ms": ms, "target_ms": 50.0,
                  "algorithmic_gbs": sbytes / ms / 1e6, "roofline_frac": sbytes / ms / 1e6 / hbm_peak}
+        # the same solve end to end: the mesh starts in (pinned) host memory, as with the header's
+        # interpolate(Mesh); the control points stay on the device, where evaluation needs them
+        try:
+            h_mesh = torch.empty(SOLVE_MESH, dtype=torch.float64, pin_memory=True)
+            h_mesh.copy_(sf)
+            np_mesh = h_mesh.numpy()
+            st.interpolate(np_mesh, into=sfn)
+            te = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                st.interpolate(np_mesh, into=sfn)   # returns when the control points are in place
+                te.append(1e3 * (time.perf_counter() - t0))
+            solve["e2e_ms"] = float(np.median(te))
+            solve["e2e_h2d_bytes"] = int(np.prod(SOLVE_MESH)) * 8
+            del h_mesh, np_mesh
+        except Exception as exc:
+            solve["e2e_ms"] = None
+            solve["e2e_error"] = str(exc)
         del sf, sfn, st
         torch.cuda.empty_cache()
         if rank == 0 and world == 1 and not args.no_cpu:
