@@ -421,6 +421,19 @@ class BSpline:
         return InterpolationFunction(_handle=out)
 
 
+def bspline(order, is_periodic, ranges, mesh, coords, derivative=None, dtype=np.float64, device=0):
+    """The flat one-shot call of the reference's MATLAB wrapper (matlab/bspline.cpp:70-141, Example.m):
+    (order, is periodic[D], range[D][2], mesh, coords[Q][D], derivative[D]) -> result[Q].  Builds the
+    function and evaluates it (or the requested mixed partial derivative) at every coordinate.  A periodic
+    axis takes its samples without the closing one, as the wrapper does (bspline.cpp:83-85)."""
+    mesh = np.asarray(mesh)
+    dim = mesh.ndim
+    fn = InterpolationFunction(int(order), mesh, [tuple(r) for r in np.asarray(ranges, dtype=np.float64).reshape(dim, 2)],
+                               [bool(p) for p in np.ravel(is_periodic)], dtype=dtype, device=device)
+    dv = None if derivative is None else [int(d) for d in np.ravel(derivative)]
+    return fn.evaluate(np.asarray(coords).reshape(-1, dim), derivatives=dv)
+
+
 def band_solve(a, rhs, p, q, cyclic, device=0):
     """BandLU factor + solve on the device (band-matrix-and-solver-test.cpp shape)."""
     a_arr, a_p = _f64(a)

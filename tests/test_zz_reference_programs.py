@@ -261,3 +261,18 @@ def test_header_additions_on_the_gpu(tmp_path, lib_built):
     r = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600)
     print(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_matlab_style_flat_call(lib_built, golden):
+    """bspline(order, is_periodic, range, mesh, coords, derivative): the MEX wrapper's signature
+    (matlab/bspline.cpp:70-141) on the reference's own 2-D golden case (interpolation-test.cpp:108-166)."""
+    import numpy as np
+    from conftest import rel_err
+    g = golden["interpolation"]
+    f2 = np.array(g["f2"]).reshape(5, 5)
+    pts = np.array(g["coords_2d"]).reshape(-1, 2)
+    v = lib_built.bspline(3, [False, False], [[0, 4], [0, 4]], f2, pts)
+    assert rel_err(v, g["vals_2d"]) < 1e-14
+    d = lib_built.bspline(3, [0, 0], [0, 4, 0, 4], f2, pts, derivative=[2, 1])
+    assert rel_err(d, g["vals_2d_derivative_x2_y1"]) < 1e-14
