@@ -14,6 +14,8 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 def _build(tmp_path, lib_built, source="drop_in_test.cpp"):
     g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_vectors.json")))["interpolation"]
+    # outputs of the reference instantiated with float values on double coordinates (make_ref_outputs_mixed.py)
+    g.update(json.load(open(os.path.join(ROOT, "tests", "golden", "ref_outputs_mixed.json"))))
     inc = tmp_path / "golden_vectors.inc"
     with open(inc, "w") as fh:
         fh.write("#include <vector>\nnamespace golden {\n")
