@@ -180,6 +180,13 @@ class ClockSampler:
         return out
 
 
+def numa_nodes_visible():
+    try:
+        return len([d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()])
+    except Exception:
+        return None
+
+
 def bind_to_gpu_numa_node(local):
     """Plumbing for the end-to-end leg: run this rank (and first-touch its pinned buffers) on the
     NUMA node its GPU hangs off.  Returns the node, or None when the platform does not say."""
@@ -202,6 +209,139 @@ def bind_to_gpu_numa_node(local):
         pass
     return None
 
+
+
+def smooth_field_slab(shape, b, e):
+    """planes [b, e) of axis 0 of smooth_field_np(shape), without building the whole mesh"""
+    axes = [np.cos(2 * np.pi * np.arange(n) / n - np.pi) for n in shape]
+    return (axes[0][b:e, None, None] * axes[1][None, :, None]) * axes[2][None, None, :]
+
+
+def timed_collective(torch, dist, world, fn, reps=5, warm=3):
+    """median over `reps` of the max-over-ranks device time of fn() (CUDA events on the current
+    stream, ranks aligned by a barrier before every repetition)"""
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(warm):
+        fn()
+    ts = []
+    for _ in range(reps):
+        sync()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ts.append(float(t.item()))
+    return float(np.median(ts)), ts
+
+
+def sharded_solve_leg(B, torch, dist, local, rank, world, single_ctrl_host):
+    """BASELINE configs[3] as it is stated: the 512^3 solve slab-sharded over the ranks, both
+    exchanges (NCCL all-to-all; sweep fused with NVLink peer stores), and the gathered control
+    points compared bit for bit with the single-GPU solve of rank 0."""
+    from bsplineinterpolation_b200.distributed import ShardedSolve3D
+    n0 = SOLVE_MESH[0]
+    sh = ShardedSolve3D(ORDER, SOLVE_MESH, [(0.0, 1.0)] * 3, device=local)
+    b, e = sh.slab0[rank], sh.slab0[rank + 1]
+    f = torch.from_numpy(smooth_field_slab(SOLVE_MESH, b, e)).to(torch.device("cuda", local))
+    res = {"mesh": list(SOLVE_MESH), "n_gpus": world, "planes_per_gpu": e - b,
+           "exchange_bytes_per_gpu": int((e - b) * SOLVE_MESH[1] * SOLVE_MESH[2] * 8 * (world - 1) / world)}
+    parity = {}
+    for name, run in (("nccl", lambda: sh.solve(f)), ("fused", lambda: sh.solve_fused(f))):
+        ms, all_ms = timed_collective(torch, dist, world, run)
+        res[name + "_ms"] = ms
+        res[name + "_ms_all"] = all_ms
+        full = sh.gather_control_points(run())
+        torch.cuda.synchronize()
+        if rank == 0 and single_ctrl_host is not None:
+            parity[name] = bool(np.array_equal(full.cpu().numpy(), single_ctrl_host))
+        del full
+        torch.cuda.empty_cache()
+    if sh.timed_out():
+        res["error"] = "a rank barrier timed out"
+    res["parity"] = (all(parity.values()) if parity else None)
+    res["parity_detail"] = parity
+    res["parity_against"] = "control points of the single-GPU solve on rank 0, numpy.array_equal (bit-identical)"
+    sbytes = 2 * 8 * 3 * float(np.prod(SOLVE_MESH))
+    res["algorithmic_gbs_aggregate"] = sbytes / min(res["nccl_ms"], res["fused_ms"]) / 1e6
+    sh.close()
+    del f
+    torch.cuda.empty_cache()
+    return res
+
+
+def sharded_fields_leg(B, torch, dist, local, rank, world):
+    """BASELINE configs[4] field-sharded: the 4 096 fields split over the ranks,
+    every rank holds the template, solves its fields and evaluates them at the same 2^20 points.
+    No collective on the data path."""
+    from bsplineinterpolation_b200.distributed import shard_range
+    dev = torch.device("cuda", local)
+    F, shape, Q = 4096, (128, 128), 1 << 20
+    fb, fe = shard_range(F, rank, world)
+    t = B.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0)] * 2, device=local)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777)                      # every rank draws the whole batch, keeps its share
+    f = torch.rand((F,) + shape, dtype=torch.float64, device=dev, generator=gen)[fb:fe].contiguous()
+    pts = torch.rand((Q, 2), dtype=torch.float64, device=dev, generator=gen)
+    fn = t.interpolate(f)
+    solve_ms, _ = timed_collective(torch, dist, world, lambda: t.interpolate(f, into=fn), reps=5, warm=1)
+    out = torch.empty((fe - fb, Q), dtype=torch.float64, device=dev)
+    eval_ms, _ = timed_collective(torch, dist, world, lambda: fn.evaluate_fields(pts, out=out), reps=3, warm=1)
+    res = {"fields_total": F, "fields_per_gpu": fe - fb, "queries": Q, "solve_ms": solve_ms,
+           "evaluate_fields_ms": eval_ms, "G_evaluations_per_s": F * Q / eval_ms / 1e6}
+    try:
+        outT = torch.empty((Q, fe - fb), dtype=torch.float64, device=dev)
+        ms2, _ = timed_collective(torch, dist, world, lambda: fn.evaluate_fields(pts, out=outT, layout="query_major"),
+                                  reps=3, warm=1)
+        res["evaluate_fields_query_major_ms"] = ms2
+        res["G_evaluations_per_s_query_major"] = F * Q / ms2 / 1e6
+        k = (fe - fb) // 2
+        one = fn.evaluate(pts, field=k)
+        scale = float(one.abs().max().item())
+        res["max_rel_diff_vs_per_field"] = max(float((out[k] - one).abs().max().item()),
+                                               float((outT[:, k] - one).abs().max().item())) / scale
+        del outT
+    except Exception as exc:
+        res["query_major_error"] = str(exc)
+    del f, pts, out, fn, t
+    torch.cuda.empty_cache()
+    return res
+
+
+def copy_ceiling(torch, dist, world, dev, h_pts, h_out, steps):
+    """The end-to-end leg's copies with no kernel at all: the same chunking (2^22 queries), three
+    streams, H2D of the points and D2H of a result-sized device buffer -- what the host<->device
+    path of THIS box allows at THIS number of ranks."""
+    qe = h_pts.shape[0]
+    chunk = min(qe, 1 << 22)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(3)]
+    d_in = [torch.empty((chunk, 3), dtype=torch.float64, device=dev) for _ in range(3)]
+    d_out = [torch.zeros((chunk, 4), dtype=torch.float64, device=dev) for _ in range(3)]
+
+    def one_pass():
+        for it, lo in enumerate(range(0, qe, chunk)):
+            hi = min(qe, lo + chunk)
+            sl = it % 3
+            with torch.cuda.stream(streams[sl]):
+                d_in[sl][: hi - lo].copy_(h_pts[lo:hi], non_blocking=True)
+                h_out[lo:hi].copy_(d_out[sl][: hi - lo], non_blocking=True)
+        torch.cuda.synchronize()
+
+    one_pass()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return world * qe * steps / float(t.item()) / 1e6
 
 # ----------------------------------------------------------------------------- other configurations
 def other_configs(B, torch, dev, hbm_peak):
@@ -238,7 +378,7 @@ def other_configs(B, torch, dev, hbm_peak):
     torch.cuda.empty_cache()
     # cfg2: 1-D order-5 periodic, 2^24 mesh points, value + first derivative; solve time beside it
     try:
-        shape, Q = (1 << 24,), 1 << 24
+        shape, Q = (1 << 24,), 1 << 26   # BASELINE configs[1]: 64M queries
         t0 = time.perf_counter()
         t = B.InterpolationFunctionTemplate(5, shape, [(0.0, 1.0)], [True], device=dev.index)
         template_ms = 1e3 * (time.perf_counter() - t0)
@@ -346,6 +486,25 @@ def run_gpu(args):
     achieved = q * B_QUERY / (kern_ms * 1e-3) / 1e9
     checksum = float(out[:: max(1, q // 4096)].sum().item())
 
+    # ---- strong scaling companion (BASELINE configs[2] as stated: 2^28 queries SPLIT over the GPUs)
+    strong = None
+    if world > 1:
+        qs = max(1, args.queries // world)
+        s_pts, s_out = pts[:qs], out[:qs]
+        for _ in range(2):
+            fn.value_grad(s_pts, out=s_out)
+        barrier()
+        a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            fn.value_grad(s_pts, out=s_out)
+        b.record()
+        barrier()
+        s_ms = max_over_ranks(a.elapsed_time(b)) / args.steps
+        strong = {"queries_total": qs * world, "queries_per_gpu": qs, "ms_per_step": s_ms,
+                  "value": qs * world / s_ms / 1e3, "unit": "Mpts/s", "scaling": "strong",
+                  "roofline_frac_per_gpu": qs * B_QUERY / (s_ms * 1e-3) / 1e9 / hbm_peak}
+
     # ---- the dominant kernel alone (eval_binned_kernel: the tile evaluation): a query plan keeps the
     # sorted records, so evaluating through it launches that kernel and nothing else
     dominant = None
@@ -393,6 +552,12 @@ def run_gpu(args):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * qe * e2e_steps / e2e_s / 1e6
     e2e_err = float(np.abs(np_out[:4096] - out[:4096].cpu().numpy()).max())
+    try:
+        ceiling = copy_ceiling(torch, dist, world, dev, h_pts, h_out, e2e_steps)
+    except Exception as exc:
+        ceiling = None
+        print("copy ceiling failed: %s" % exc, file=sys.stderr)
+    del h_pts, h_out, np_pts, np_out
 
     # ---- second half of the metric: 512^3 control-point solve (device resident), rank-local
     solve = None
@@ -432,8 +597,17 @@ def run_gpu(args):
         except Exception as exc:
             solve["e2e_ms"] = None
             solve["e2e_error"] = str(exc)
+        single_ctrl = None
+        if world > 1 and rank == 0:
+            single_ctrl = sfn.control_points()     # host copy, for the sharded solve's parity check
         del sf, sfn, st
         torch.cuda.empty_cache()
+        if world > 1:
+            try:
+                solve["sharded"] = sharded_solve_leg(B, torch, dist, local, rank, world, single_ctrl)
+            except Exception as exc:
+                solve["sharded"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            del single_ctrl
         if rank == 0 and world == 1 and not args.no_cpu:
             solve["cpu_reference"] = cpu_reference_solve()
 
@@ -451,6 +625,12 @@ def run_gpu(args):
     other = None
     if world == 1 and not args.no_other:
         other = other_configs(B, torch, dev, hbm_peak)
+    fields_sharded = None
+    if world > 1 and not args.no_other:
+        try:
+            fields_sharded = sharded_fields_leg(B, torch, dist, local, rank, world)
+        except Exception as exc:
+            fields_sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
         traffic = None
@@ -468,7 +648,8 @@ def run_gpu(args):
             "config": {"workload": "cfg3: 3D cubic 256^3 mesh, %d uniform-random queries per GPU per step, "
                                    "value+gradient, coefficients replicated, queries sharded" % q,
                        "mesh": list(MESH), "order": ORDER, "queries_per_gpu": q,
-                       "l2": "inputs+outputs (%.1f GB per step) exceed the 126 MB L2" % (q * B_STREAM / 1e9)},
+                       "l2": "inputs+outputs (%.1f GB per step) exceed the 126 MB L2" % (q * B_STREAM / 1e9),
+                       "strong": strong},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
                          "kernel_ms": kern_ms, "kernel": "whole evaluate call (key_count, scans, scatter, eval_binned)",
@@ -479,11 +660,17 @@ def run_gpu(args):
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "Mpts/s", "h2d_bytes_per_step": qe * 24, "d2h_bytes_per_step": qe * 32,
                     "queries_per_gpu": qe, "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_err,
-                    "numa_node_rank0": numa_node},
+                    "copy_ceiling": ceiling,
+                    "frac_of_ceiling": (e2e_value / ceiling) if ceiling else None,
+                    "copy_ceiling_note": "the same host<->device copies (2^22-query chunks, 3 streams, both directions) "
+                                         "with no kernel, all ranks at once, max over ranks",
+                    "numa_node_rank0": numa_node, "numa_nodes_visible": numa_nodes_visible(),
+                    "host_cores": os.cpu_count()},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "solve": solve,
             "other_configs": other,
+            "cfg5_field_sharded": fields_sharded,
             "checksum": checksum,
         }
         emit(line)

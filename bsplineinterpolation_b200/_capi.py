@@ -25,6 +25,15 @@ SIGNATURES = {
     "bspl_template_sweep_axis": (C.c_int, [_vp, C.c_int, _vp, _i64p, _i64p, C.c_int64, _vp]),
     "bspl_template_sweep_axis_exchange": (C.c_int, [_vp, C.c_int, _vp, _i64p, _i64p, C.c_int64, C.c_int, _i64p,
                                                     _vpp, _ip, _i64p, _i64p, _vp]),
+    "bspl_sharded_solve_create": (C.c_int, [_vp, C.c_int, C.c_int, _vpp]),
+    "bspl_sharded_solve_destroy": (None, [_vp]),
+    "bspl_sharded_solve_layout": (C.c_int, [_vp, _i64p, _i64p]),
+    "bspl_sharded_solve_handle": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "bspl_sharded_solve_connect": (C.c_int, [_vp, C.POINTER(C.c_ubyte)]),
+    "bspl_sharded_solve_run": (C.c_int, [_vp, _vp, _vpp, _vp]),
+    "bspl_sharded_solve_pack": (C.c_int, [_vp, _vp, _vpp, _vpp, _i64p, _i64p, _vp]),
+    "bspl_sharded_solve_finish": (C.c_int, [_vp, _vpp, _vp]),
+    "bspl_sharded_solve_status": (C.c_int, [_vp, _ip]),
     "bspl_ipc_alloc": (C.c_int, [C.c_int, C.c_int64, _vpp, C.POINTER(C.c_ubyte)]),
     "bspl_ipc_open": (C.c_int, [C.c_int, C.POINTER(C.c_ubyte), _vpp]),
     "bspl_ipc_close": (C.c_int, [C.c_int, _vp]),
@@ -35,12 +44,14 @@ SIGNATURES = {
     "bspl_function_clone": (C.c_int, [_vp, _vpp]),
     "bspl_function_destroy": (None, [_vp]),
     "bspl_function_info": (C.c_int, [_vp, _ip, _ip, _ip, _i64p, _i64p, _ip, _ip, _i64p, _dp, _dp]),
+    "bspl_function_device": (C.c_int, [_vp, _ip]),
     "bspl_function_knots": (C.c_int, [_vp, C.c_int, _dp, C.c_int64]),
     "bspl_function_control_points": (C.c_int, [_vp, C.c_int64, _vp]),
     "bspl_evaluate": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _ip, _vp, C.c_int, _vp]),
     "bspl_evaluate_at": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _ip, _vp, _i64p]),
     "bspl_evaluate_value_grad": (C.c_int, [_vp, C.c_int64, _vp, C.c_int64, _vp, C.c_int, _vp]),
     "bspl_evaluate_fields": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, _vp]),
+    "bspl_evaluate_fields_query_major": (C.c_int, [_vp, _vp, C.c_int64, _ip, _vp, C.c_int, _vp]),
     "bspl_query_plan_create": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
     "bspl_template_query_plan_create": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, _vp, _vpp]),
     "bspl_query_plan_evaluate": (C.c_int, [_vp, _vp, C.c_int64, _ip, C.c_int, _vp, C.c_int, _vp]),
@@ -53,6 +64,7 @@ SIGNATURES = {
     "bspl_host_axis_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _ip,
                                         _dp, _dp, _dp, _dp, _dp]),
     "bspl_set_eval_path": (C.c_int, [C.c_int]),
+    "bspl_set_fields_path": (C.c_int, [C.c_int]),
     "bspl_launch_count": (C.c_int64, []),
     "bspl_reset_launch_count": (None, []),
     "bspl_last_kernel_ms": (C.c_double, []),

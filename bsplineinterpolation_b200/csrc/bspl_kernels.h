@@ -59,6 +59,42 @@ bool fields_smem_eligible(const EvalArgs<R>& a);
 template <typename R>
 cudaError_t launch_eval_fields_smem(const EvalArgs<R>& a, cudaStream_t s);
 
+// Many fields at one query set as a per-cell contraction with query-major results (bspl_contract.cu).
+struct FieldsScratch {
+    uint32_t* counts;      // [n_keys] queries per cell
+    uint32_t* cursor;      // [n_keys]
+    uint32_t* idx_sorted;  // [q] original index of the query at each sorted position
+    void* w_sorted;        // [q][K] tensor-product weights in cell order
+    uint32_t* work;        // (key, begin, end) triples
+    uint32_t* n_work;
+    uint32_t* next_unit;
+};
+template <typename R>
+struct FieldsContractArgs {
+    int dim, order, K;          // K = (order+1)^dim stencil terms
+    AxisParams<R> ax[kMaxDim];
+    int deriv[kMaxDim];
+    int n_keys;                 // padded elements per field: a cell's key is the offset of its first control point
+    int chunk;                  // queries per work item (fields_query_chunk)
+    const R* pts;               // [q][dim]                         (sort phase)
+    long long q;
+    const R* coef_t;            // [n_keys][n_fields] field-minor   (contract phase)
+    int n_fields;
+    int field_begin, field_end; // fields evaluated by this launch
+    R* out;                     // (query, field) at query * out_stride + field - field_begin
+    long long out_stride;
+    int off[64];                // offset of stencil term k from the cell's first control point, last axis fastest
+};
+int fields_query_chunk(int K);
+size_t fields_scratch_bytes(long long q, int n_keys, int K, size_t elem, size_t* offsets /*[6]*/);
+FieldsScratch fields_scratch_view(void* base, long long q, int n_keys, int K, size_t elem);
+bool fields_contract_supported(int dim, int order);
+template <typename R>
+cudaError_t launch_fields_sort(const FieldsContractArgs<R>& a, const FieldsScratch& sc, cudaStream_t s);
+// cudaErrorNotSupported: alignment of out / coef_t / n_fields does not allow the vector accesses
+template <typename R>
+cudaError_t launch_fields_contract(const FieldsContractArgs<R>& a, const FieldsScratch& sc, cudaStream_t s);
+
 // span - order per axis, int32 [q][dim]
 template <typename R>
 cudaError_t launch_locate(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s);
@@ -157,10 +193,26 @@ struct ExchangeDest {
     R* base[kMaxPeers];         // rank r's buffer, already offset to this rank's block in it
     long long ms[kMaxPeers][3]; // strides of the three outer line indices in rank r's buffer
     long long ls[kMaxPeers];    // stride between consecutive rows in rank r's buffer
+    // the middle outer index lands at (i1 + i1_offset) mod i1_mod in the destination (i1_mod == 0: as it is):
+    // the slab offset of this rank plus the rotation of a periodic slab axis (InterpolationTemplate.hpp:455-459)
+    int i1_offset, i1_mod;
 };
 template <typename R>
 cudaError_t launch_sweep_exchange(const AxisLU<R>& lu, const SweepGeom& g, R* data, const ExchangeDest<R>& dest,
                                   cudaStream_t s);
+
+// Stream-ordered barrier between the ranks of one node (one process per GPU): every rank's kernel
+// bumps its own epoch counter, stores the epoch into its slot of every peer's flag array
+// (peer-mapped memory, release at system scope) and waits until all of its own slots have
+// reached the epoch.  No host synchronisation; gives up after `timeout_cycles` and sets *status.
+struct RankBarrier {
+    int rank, n_ranks;
+    unsigned int* flags[kMaxPeers];  // flags[r]: rank r's array of kMaxPeers slots (this rank's own for r == rank)
+    unsigned int* epoch;             // this rank's barrier count (device memory)
+    int* status;                     // set to 1 on timeout (device memory)
+    long long timeout_cycles;
+};
+cudaError_t launch_rank_barrier(const RankBarrier& b, cudaStream_t s);
 
 // Batched transpose of the last two axes through shared memory:
 //   dst[(b0, b1), rot_q(q), rot_p(p)] = src[(b0, b1), p, q]     (src q-contiguous, dst p-contiguous)

@@ -5,9 +5,11 @@ shards into independent units:
   * evaluation      -- queries split evenly over ranks, coefficients replicated, no collective
                        (SURVEY 8(e) row 1; bench.py);
   * many fields     -- fields split over ranks, every rank holds the (tiny) LU factors (row 2);
-  * one 3-D solve   -- slab-sharded along axis 0: sweep axes 2 and 1 locally, one all-to-all
-                       re-shards to slabs along axis 1, sweep axis 0 (row 3).  The sweeps are
-                       bspl_template_sweep_axis launches; the exchange is NCCL over NVLink.
+  * one 3-D solve   -- slab-sharded along axis 0: sweep axes 2 and 1 locally, one exchange
+                       re-shards to slabs along axis 1, sweep axis 0 (row 3).  The whole sequence is
+                       the library's bspl_sharded_solve_* plan: either one kernel that sweeps axis 1
+                       and stores the solved rows into the peers' buffers over NVLink, or the same
+                       kernel packing the blocks of an NCCL all-to-all.
 
 The reference has no counterpart (single process, DedicatedThreadPool.hpp); the arithmetic
 per line is that of solve_for_control_points_ (InterpolationTemplate.hpp:448-580), whose
@@ -100,11 +102,12 @@ def reshard_axis1_to_axis0(local, n1, group=None):
 
 
 class _DevicePtr:
-    """A raw device allocation seen as a float64 CUDA array (plumbing: lets torch view memory that
-    the library allocated for IPC)."""
+    """A raw device allocation seen as a CUDA array (plumbing: lets torch view memory that the
+    library owns)."""
 
-    def __init__(self, ptr, shape):
-        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": "<f8",
+    def __init__(self, ptr, shape, dtype=np.float64):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape),
+                                         "typestr": "<f8" if np.dtype(dtype) == np.float64 else "<f4",
                                          "data": (int(ptr), False), "version": 3, "strides": None}
 
     def tensor(self, device):
@@ -113,143 +116,142 @@ class _DevicePtr:
 
 
 class ShardedSolve3D:
-    """Slab-sharded control-point solve of ONE 3-D field over the ranks of `group`."""
+    """Slab-sharded control-point solve of ONE 3-D field over the ranks of `group`: a thin holder of
+    the library's plan (bspl_sharded_solve_*, include/bspline_b200.h).  The sweeps, the exchange and
+    the rank barriers are launches of the C library on the current CUDA stream; torch.distributed
+    only carries the 64-byte IPC handles at set-up and, for solve(), the NCCL all-to-all."""
 
-    def __init__(self, order, shape, ranges, periodicity=None, device=0, group=None):
+    def __init__(self, order, shape, ranges, periodicity=None, device=0, group=None, dtype=np.float64):
+        import ctypes as C
+        import torch.distributed as dist
+        from ._capi import check, lib
         from .interpolation import InterpolationFunctionTemplate
         assert len(shape) == 3
         self.order, self.shape = int(order), tuple(int(s) for s in shape)
         self.periodicity = [bool(p) for p in (periodicity or [False] * 3)]
         self.group = group
+        self.device = int(device)
+        self.dtype = np.dtype(dtype)
+        self.rank, self.world = _rank_world(group)
         # every rank factors the three small collocation matrices itself
-        self.template = InterpolationFunctionTemplate(order, shape, ranges, self.periodicity, device=device)
+        self.template = InterpolationFunctionTemplate(order, shape, ranges, self.periodicity, dtype=dtype, device=device)
+        h = C.c_void_p()
+        check(lib().bspl_sharded_solve_create(self.template._h, self.rank, self.world, C.byref(h)))
+        self._h = h
+        b0 = (C.c_int64 * (self.world + 1))()
+        b1 = (C.c_int64 * (self.world + 1))()
+        check(lib().bspl_sharded_solve_layout(self._h, b0, b1))
+        self.slab0, self.slab1 = list(b0), list(b1)
+        # publish the receive buffers (CUDA IPC) and map the peers'
+        handle = (C.c_ubyte * 64)()
+        check(lib().bspl_sharded_solve_handle(self._h, handle))
+        if self.world > 1:
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, bytes(handle), group=group)
+            blob = (C.c_ubyte * (64 * self.world)).from_buffer_copy(b"".join(everyone))
+            check(lib().bspl_sharded_solve_connect(self._h, blob))
+            dist.barrier(group=group)
+        else:
+            check(lib().bspl_sharded_solve_connect(self._h, None))
 
-    def _shift(self, x, axis):
+    def close(self):
+        """Unmap the peers' buffers and free this rank's (collective: nobody may still be writing)."""
         import torch
-        # periodic right-hand sides are rotated by O/2 (InterpolationTemplate.hpp:455-459)
-        if self.periodicity[axis] and self.order // 2:
-            return torch.roll(x, shifts=self.order // 2, dims=axis)
-        return x
+        import torch.distributed as dist
+        from ._capi import lib
+        if getattr(self, "_h", None):
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            lib().bspl_sharded_solve_destroy(self._h)
+            self._h = None
 
-    def _local_sweeps(self, f_slab):
-        """Working copy of the slab (periodic axes 1, 2 rotated) with axis 2 solved: lines along the
-        contiguous axis go through the TMA-tiled sweep (bspl_solve.cu) in place."""
+    def __del__(self):
+        try:
+            from ._capi import lib
+            if getattr(self, "_h", None):
+                lib().bspl_sharded_solve_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # kept for callers of the round-1 interface: the buffers now belong to the plan
+    def enable_fused_exchange(self):
+        pass
+
+    def close_fused_exchange(self):
+        pass
+
+    def _slab_ptr(self, f_slab):
+        import ctypes as C
+        import torch
+        want = torch.float64 if self.dtype == np.float64 else torch.float32
         n0, n1, n2 = self.shape
-        w = self._shift(self._shift(f_slab, 2), 1)
-        w = w.clone() if w.data_ptr() == f_slab.data_ptr() else w.contiguous()
-        self.template.sweep_axis(2, w, (1, f_slab.shape[0], n1), (0, n1 * n2, n2), 1)
-        return w
+        exp = (self.slab0[self.rank + 1] - self.slab0[self.rank], n1, n2)
+        if not (f_slab.is_cuda and f_slab.dtype == want and f_slab.is_contiguous() and tuple(f_slab.shape) == exp):
+            raise ValueError("f_slab must be a contiguous %s CUDA tensor of shape %s" % (want, exp))
+        if f_slab.device.index != self.device:
+            raise ValueError("f_slab on %s, the plan on cuda:%d" % (f_slab.device, self.device))
+        return C.c_void_p(f_slab.data_ptr()), C.c_void_p(torch.cuda.current_stream(f_slab.device).cuda_stream)
+
+    def _view(self, ptr, shape):
+        return _DevicePtr(ptr, shape, self.dtype).tensor(self.device)
+
+    def solve_fused(self, f_slab):
+        """One call, no host synchronisation: the axis-1 sweep stores its solved rows straight into
+        their owners' buffers over NVLink (bspl_sharded_solve_run).  Returns this rank's slab of
+        axis 1, [n0, n1_loc, n2]: a view of the plan's buffer, valid until the next solve."""
+        import ctypes as C
+        from ._capi import check, lib
+        fp, sp = self._slab_ptr(f_slab)
+        out = C.c_void_p()
+        check(lib().bspl_sharded_solve_run(self._h, fp, C.byref(out), sp))
+        n0, n1, n2 = self.shape
+        return self._view(out.value, (n0, self.slab1[self.rank + 1] - self.slab1[self.rank], n2))
 
     def solve(self, f_slab, back_to_axis0=False):
-        """f_slab: CUDA tensor [n0_loc, n1, n2], this rank's axis-0 slab of the mesh.
-        Returns the control points as a slab of axis 1, [n0, n1_loc, n2] (or of axis 0)."""
-        n0, n1, n2 = self.shape
-        n0_loc = f_slab.shape[0]
-        t = self.template
-        w = self._local_sweeps(f_slab)
-        t.sweep_axis(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2)
-        y = reshard_axis0_to_axis1(w, n0, self.group)
-        y = self._shift(y, 0).contiguous()
-        n1_loc = y.shape[1]
-        t.sweep_axis(0, y, (1, 1, n1_loc * n2), (0, 0, 1), n1_loc * n2)
-        return reshard_axis1_to_axis0(y, n1, self.group) if back_to_axis0 else y
-
-    # ---- fused exchange: the last local sweep stores straight into the owners' buffers ----
-    def enable_fused_exchange(self):
-        """Allocate this rank's receive buffer [n0][n1_loc][n2] (bspl_ipc_alloc) and map every
-        peer's buffer for access from this rank's GPU (bspl_ipc_open).  Collective."""
+        """The same solve with the exchange as an NCCL all-to-all: bspl_sharded_solve_pack (sweeps +
+        packed send blocks), all_to_all_single, bspl_sharded_solve_finish (axis-0 sweep)."""
         import ctypes as C
         import torch
         import torch.distributed as dist
         from ._capi import check, lib
-        rank, world = _rank_world(self.group)
+        fp, sp = self._slab_ptr(f_slab)
+        send, recv, out = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        sc = (C.c_int64 * self.world)()
+        rc = (C.c_int64 * self.world)()
+        check(lib().bspl_sharded_solve_pack(self._h, fp, C.byref(send), C.byref(recv), sc, rc, sp))
         n0, n1, n2 = self.shape
-        s1 = shard_sizes(n1, world)
-        dev = torch.cuda.current_device()
-        self._dev = dev
-        handle = (C.c_ubyte * 64)()
-        ptr = C.c_void_p()
-        check(lib().bspl_ipc_alloc(dev, n0 * s1[rank] * n2 * 8, C.byref(ptr), handle))
-        self._own_ptr = ptr.value
-        self._recv = _DevicePtr(ptr.value, (n0, s1[rank], n2)).tensor(dev)
-        self._opened = []
-        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
-        if world == 1:
-            self._peers = [self._recv]
-            return
-        everyone = [None] * world
-        dist.all_gather_object(everyone, bytes(handle), group=self.group)
-        self._peers = []
-        for r in range(world):
-            if r == rank:
-                self._peers.append(self._recv)
-                continue
-            h = (C.c_ubyte * 64).from_buffer_copy(everyone[r])
-            p = C.c_void_p()
-            check(lib().bspl_ipc_open(dev, h, C.byref(p)))
-            self._opened.append(p.value)
-            self._peers.append(_DevicePtr(p.value, (n0, s1[r], n2)).tensor(dev))
+        n1_loc = self.slab1[self.rank + 1] - self.slab1[self.rank]
+        if self.world > 1:
+            tsend = self._view(send.value, (int(sum(sc)),))
+            trecv = self._view(recv.value, (int(sum(rc)),))
+            dist.all_to_all_single(trecv, tsend, output_split_sizes=[int(c) for c in rc],
+                                   input_split_sizes=[int(c) for c in sc], group=self.group)
+        else:  # one rank: the "exchange" is a copy on the same stream
+            self._view(recv.value, (int(sum(rc)),)).copy_(self._view(send.value, (int(sum(sc)),)))
+        check(lib().bspl_sharded_solve_finish(self._h, C.byref(out), sp))
+        y = self._view(out.value, (n0, n1_loc, n2))
+        return reshard_axis1_to_axis0(y, n1, self.group) if back_to_axis0 else y
 
-    def close_fused_exchange(self):
-        """Unmap the peers' buffers, then (after a barrier) free this rank's.  Collective."""
-        import torch
-        import torch.distributed as dist
+    def timed_out(self):
+        import ctypes as C
         from ._capi import check, lib
-        torch.cuda.synchronize()
-        self._peers = []
-        for p in getattr(self, "_opened", []):
-            check(lib().bspl_ipc_close(self._dev, p))
-        self._opened = []
-        if _rank_world(self.group)[1] > 1:
-            dist.barrier(group=self.group)
-        if getattr(self, "_own_ptr", None):
-            self._recv = None
-            check(lib().bspl_ipc_free(self._dev, self._own_ptr))
-            self._own_ptr = None
-
-    def solve_fused(self, f_slab):
-        """As solve(), but the axis-1 sweep writes its solved rows directly into the receive buffers
-        of their owners over NVLink (bspl_template_sweep_axis_exchange): no pack, no NCCL
-        all-to-all, no unpack.  Returns this rank's slab of axis 1, [n0, n1_loc, n2]; the buffer
-        is reused by the next call."""
-        import torch
-        import torch.distributed as dist
-        rank, world = _rank_world(self.group)
-        n0, n1, n2 = self.shape
-        n0_loc = f_slab.shape[0]
-        x0 = shard_range(n0, rank, world)[0]
-        s1 = shard_sizes(n1, world)
-        t = self.template
-        w = self._local_sweeps(f_slab)
-        if world > 1:
-            # stream-ordered barrier (a one-element NCCL all-reduce, no host synchronisation): every
-            # rank has consumed its previous result before anyone overwrites the buffers
-            dist.all_reduce(self._flag, group=self.group)
-        split = np.concatenate([[0], np.cumsum(s1)])
-        t.sweep_axis_exchange(1, w, (1, n0_loc, n2), (0, n1 * n2, 1), n2, split,
-                              [self._peers[r][x0:] for r in range(world)], [-1] * world,
-                              [(0, s1[r] * n2, 1) for r in range(world)], [n2] * world)
-        if world > 1:
-            # every rank's exchange kernel has completed (its peer stores are visible at kernel end)
-            dist.all_reduce(self._flag, group=self.group)
-        y = self._recv
-        if self.periodicity[0] and self.order // 2:
-            y = self._shift(y, 0).contiguous()
-        n1_loc = y.shape[1]
-        t.sweep_axis(0, y, (1, 1, n1_loc * n2), (0, 0, 1), n1_loc * n2)
-        return y
+        flag = C.c_int(0)
+        check(lib().bspl_sharded_solve_status(self._h, C.byref(flag)))
+        return bool(flag.value)
 
     def gather_function(self, ctrl_axis1_slab):
         """All-gather the solved slabs and build a replicated InterpolationFunction."""
+        return self.template.function_from_control_points(self.gather_control_points(ctrl_axis1_slab))
+
+    def gather_control_points(self, ctrl_axis1_slab):
         import torch
         import torch.distributed as dist
-        world = _rank_world(self.group)[1]
-        if world == 1:
-            return self.template.function_from_control_points(ctrl_axis1_slab.contiguous())
+        if self.world == 1:
+            return ctrl_axis1_slab.contiguous()
         n0, n1, n2 = self.shape
-        s1 = shard_sizes(n1, world)
-        parts = [torch.empty((n0, s1[r], n2), dtype=ctrl_axis1_slab.dtype, device=ctrl_axis1_slab.device)
-                 for r in range(world)]
+        parts = [torch.empty((n0, self.slab1[r + 1] - self.slab1[r], n2), dtype=ctrl_axis1_slab.dtype,
+                             device=ctrl_axis1_slab.device) for r in range(self.world)]
         dist.all_gather(parts, ctrl_axis1_slab.contiguous(), group=self.group)
-        full = torch.cat(parts, dim=1).contiguous()
-        return self.template.function_from_control_points(full)
+        return torch.cat(parts, dim=1).contiguous()

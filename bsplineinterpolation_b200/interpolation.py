@@ -50,21 +50,41 @@ def _f64(v):
     return a, a.ctypes.data_as(C.POINTER(C.c_double))
 
 
-def _split_ranges(dim, ranges):
+def _split_ranges(dim, ranges, shape=None, periodicity=None):
     """ranges[d] is (x_min, x_max) -> uniform axis, or a 1-D coordinate array ->
-    non-uniform axis (the value-pair / iterator-pair overloads of the reference)."""
+    non-uniform axis (the value-pair / iterator-pair overloads of the reference).
+    A coordinate array must hold shape[d] (+1 on a periodic axis: the closing abscissa)
+    values, as the reference asserts (Interpolation.hpp:541); a 2-element list on an axis
+    that is not 2 points long is read as (min, max)."""
     if len(ranges) != dim:
         raise ValueError("one range per dimension is required")
     lo, hi, coords = [], [], []
-    for r in ranges:
+    for d, r in enumerate(ranges):
         arr = np.asarray(r, dtype=np.float64)
-        if arr.ndim == 1 and arr.size == 2 and isinstance(r, tuple):
+        want = None if shape is None else int(shape[d]) + int(bool(periodicity[d]) if periodicity is not None else 0)
+        pair = arr.ndim == 1 and arr.size == 2 and (isinstance(r, tuple) or (want is not None and want != 2))
+        if pair:
             lo.append(arr[0]); hi.append(arr[1]); coords.append(None)
         elif arr.ndim == 1 and arr.size >= 2:
+            if want is not None and arr.size != want:
+                raise ValueError("axis %d: coordinate array has %d values, the mesh needs %d%s"
+                                 % (d, arr.size, want, " (periodic: closing abscissa included)"
+                                    if periodicity is not None and periodicity[d] else ""))
             lo.append(arr[0]); hi.append(arr[-1]); coords.append(np.ascontiguousarray(arr))
         else:
             raise ValueError("range must be a (min, max) tuple or a coordinate array")
     return lo, hi, coords
+
+
+def _check_device_out(out, dtype, shape, device=None):
+    """A caller-supplied CUDA `out` is written through its raw pointer: it must be a contiguous
+    tensor of the spline's dtype with exactly the result's element count, on the right device."""
+    if not _is_device(out):
+        raise TypeError("out must be a CUDA tensor when the points are on the device")
+    if out.dtype != dtype or not out.is_contiguous() or out.numel() != int(np.prod(shape)):
+        raise ValueError("out must be a contiguous %s CUDA tensor of %s elements" % (dtype, tuple(shape)))
+    if device is not None and out.device != device:
+        raise ValueError("out lives on %s, the points on %s" % (out.device, device))
 
 
 class InterpolationFunction:
@@ -105,6 +125,13 @@ class InterpolationFunction:
         self._uniform = [bool(uni[d]) for d in range(self.dim)]
         self._n_knots = [nk[d] for d in range(self.dim)]
         self._range = [(lo[d], hi[d]) for d in range(self.dim)]
+        dev = C.c_int(-1)
+        check(L.bspl_function_device(self._h, C.byref(dev)))
+        self.device = dev.value
+
+    def _check_device(self, t):
+        if t.device.index != self.device:
+            raise ValueError("tensor on %s, the spline lives on cuda:%d" % (t.device, self.device))
 
     def __del__(self):
         try:
@@ -149,10 +176,13 @@ class InterpolationFunction:
             pts = points.contiguous()
             if pts.dtype != (torch.float64 if self.dtype == np.float64 else torch.float32):
                 raise TypeError("device points must have the spline's dtype")
+            self._check_device(pts)
             q = pts.numel() // self.dim
             shape = ((fields,) if fields > 1 else ()) + ((q, n_out) if n_out > 1 else (q,))
             if out is None:
                 out = torch.empty(shape, dtype=pts.dtype, device=pts.device)
+            else:
+                _check_device_out(out, pts.dtype, shape, pts.device)
             sp = stream if stream is not None else torch.cuda.current_stream(pts.device).cuda_stream
             return pts, out, q, C.c_void_p(pts.data_ptr()), C.c_void_p(out.data_ptr()), 1, C.c_void_p(sp)
         pts = np.ascontiguousarray(points, dtype=self.dtype).reshape(-1, self.dim)
@@ -204,9 +234,23 @@ class InterpolationFunction:
         check(lib().bspl_evaluate_value_grad(self._h, field, pp, q, op, dev, sp))
         return out
 
-    def evaluate_fields(self, points, out=None, stream=None):
-        """One query set on every field: [n_fields][q]."""
+    def evaluate_fields(self, points, out=None, stream=None, layout="field_major", derivatives=None):
+        """One query set on every field.  layout "field_major": [n_fields][q], as if every field had been
+        evaluated on its own; "query_major": [q][n_fields], every query's values side by side (what the
+        reference returns for a vector-valued T) -- the layout the many-field kernel produces directly."""
+        if layout not in ("field_major", "query_major"):
+            raise ValueError("layout must be 'field_major' or 'query_major'")
         pts, out, q, pp, op, dev, sp = self._marshal(points, out, 1, fields=self.n_fields, stream=stream)
+        if layout == "query_major":
+            dv = None
+            if derivatives is not None:
+                if len(derivatives) != self.dim:
+                    raise ValueError("one derivative order per dimension")
+                _keep, dv = _i32(derivatives)
+            check(lib().bspl_evaluate_fields_query_major(self._h, pp, q, dv, op, dev, sp))
+            return out.reshape(q, self.n_fields) if not _is_device(out) else out.view(q, self.n_fields)
+        if derivatives is not None:
+            raise ValueError("derivatives of all fields at once: use layout='query_major'")
         check(lib().bspl_evaluate_fields(self._h, pp, q, op, dev, sp))
         return out.reshape(self.n_fields, q) if not _is_device(out) else out.view(self.n_fields, q)
 
@@ -229,10 +273,12 @@ class QueryPlan:
 
     def __init__(self, fn, points, stream=None):
         self._h = None
-        self.dim, self.dtype = fn.dim, fn.dtype
+        self.dim, self.dtype, self.device = fn.dim, fn.dtype, fn.device
         if _is_device(points):
             import torch
             pts = points.contiguous()
+            if pts.device.index != fn.device:
+                raise ValueError("points on %s, the spline lives on cuda:%d" % (pts.device, fn.device))
             self.q = pts.numel() // fn.dim
             sp = stream if stream is not None else torch.cuda.current_stream(pts.device).cuda_stream
             ptr, dev, sp = C.c_void_p(pts.data_ptr()), 1, C.c_void_p(sp)
@@ -256,15 +302,20 @@ class QueryPlan:
             _keep, dv = _i32(derivatives)
         if device_out or _is_device(out):
             import torch
+            tdt = torch.float64 if self.dtype == np.float64 else torch.float32
             if out is None:
-                out = torch.empty(shape, dtype=torch.float64 if self.dtype == np.float64 else torch.float32,
-                                  device="cuda")
+                out = torch.empty(shape, dtype=tdt, device=torch.device("cuda", self.device))
+            else:
+                _check_device_out(out, tdt, shape, torch.device("cuda", self.device))
             sp = stream if stream is not None else torch.cuda.current_stream(out.device).cuda_stream
             check(lib().bspl_query_plan_evaluate(self._h, fn._h, field, dv, int(value_grad),
                                                  C.c_void_p(out.data_ptr()), 1, C.c_void_p(sp)))
             return out
         if out is None:
             out = np.empty(shape, dtype=self.dtype)
+        elif (not isinstance(out, np.ndarray) or out.dtype != self.dtype or not out.flags.c_contiguous
+              or out.size != int(np.prod(shape))):
+            raise ValueError("out must be a C-contiguous %s array of %s elements" % (self.dtype, shape))
         check(lib().bspl_query_plan_evaluate(self._h, fn._h, field, dv, int(value_grad),
                                              out.ctypes.data_as(C.c_void_p), 0, None))
         return out
@@ -289,7 +340,7 @@ class InterpolationFunctionTemplate:
             periodicity = [False] * dim
         if np.ndim(periodicity) == 0:
             periodicity = [bool(periodicity)] * dim
-        lo, hi, coords = _split_ranges(dim, ranges)
+        lo, hi, coords = _split_ranges(dim, ranges, shape, periodicity)
         self.dim, self.order, self.shape = dim, int(order), shape
         self.dtype = _NP[_dtype_code(dtype)]
         self.device = device
@@ -468,6 +519,12 @@ def reset_launch_count():
 
 def last_kernel_ms():
     return lib().bspl_last_kernel_ms()
+
+
+def set_fields_path(path):
+    """Many-field evaluation: "auto", "gather" (per-query gather out of shared memory) or "contract"
+    (cell-sorted contraction)."""
+    check(lib().bspl_set_fields_path({"auto": 0, "gather": 1, "contract": 2}.get(path, path)))
 
 
 def set_eval_path(path):

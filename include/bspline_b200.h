@@ -101,6 +101,40 @@ int bspl_template_sweep_axis_exchange(const bspl_template* t, int axis, void* da
                                       const int64_t* split, void* const* peer_base,
                                       const int* peer_device, const int64_t* peer_ms,
                                       const int64_t* peer_ls, void* stream);
+/* ---- slab-sharded solve of ONE 3-D field over the GPUs of a node ---------------------------------
+ * No reference counterpart (the reference is one process; its parallel unit is the
+ * INTP_MULTITHREAD line loop, InterpolationTemplate.hpp:547-572).  The arithmetic per line is
+ * solve_for_control_points_'s (:448-580); its per-axis solves commute, so a mesh cut into slabs of
+ * axis 0 sweeps axes 2 and 1 locally, re-shards to slabs of axis 1 and sweeps axis 0 there.  One
+ * process per GPU; rank r of n_ranks owns planes [slab0[r], slab0[r+1]) of axis 0 before and
+ * [slab1[r], slab1[r+1]) of axis 1 after the exchange (even split, remainder to the low ranks).
+ * Every rank creates its plan from its own template (same mesh, its own device), publishes the
+ * 64-byte handle of its receive buffer to the others by any means, and connects. */
+typedef struct bspl_sharded_solve bspl_sharded_solve;
+int bspl_sharded_solve_create(const bspl_template* t, int rank, int n_ranks, bspl_sharded_solve** out);
+void bspl_sharded_solve_destroy(bspl_sharded_solve* s);   /* the template must outlive the plan */
+/* slab boundaries, n_ranks + 1 entries each (either may be NULL) */
+int bspl_sharded_solve_layout(const bspl_sharded_solve* s, int64_t* slab0, int64_t* slab1);
+int bspl_sharded_solve_handle(const bspl_sharded_solve* s, unsigned char handle_out[64]);
+/* handles: n_ranks * 64 bytes, entry r from rank r (the own entry is ignored; NULL when n_ranks == 1) */
+int bspl_sharded_solve_connect(bspl_sharded_solve* s, const unsigned char* handles);
+/* The whole solve on `stream`, no host synchronisation: f_slab is this rank's DEVICE slab
+ * [slab0 planes][n1][n2] of the mesh; *ctrl_slab receives a device pointer to this rank's slab
+ * [n0][slab1 planes][n2] of the control points, owned by the plan and valid until its next run.
+ * The axis-1 sweep stores its solved rows straight into the owners' buffers (peer-mapped memory,
+ * NVLink stores) -- sweep and exchange are one kernel -- and the ranks meet at two stream-ordered
+ * flag barriers.  Collective: every rank calls it the same number of times. */
+int bspl_sharded_solve_run(bspl_sharded_solve* s, const void* f_slab, void** ctrl_slab, void* stream);
+/* The same solve around a caller-run all-to-all (NCCL): pack() sweeps axes 2 and 1 and leaves the
+ * blocks for the ranks back to back in *send (send_counts[r] elements for rank r); the caller
+ * exchanges them into *recv (recv_counts[r] elements from rank r, in rank order) on the same
+ * stream; finish() sweeps axis 0 and returns the slab as run() does. */
+int bspl_sharded_solve_pack(bspl_sharded_solve* s, const void* f_slab, void** send, void** recv,
+                            int64_t* send_counts, int64_t* recv_counts, void* stream);
+int bspl_sharded_solve_finish(bspl_sharded_solve* s, void** ctrl_slab, void* stream);
+/* *timed_out != 0: a flag barrier gave up waiting for a peer (~10 s); results are invalid.  Synchronises. */
+int bspl_sharded_solve_status(bspl_sharded_solve* s, int* timed_out);
+
 /* Device buffers shareable between the ranks of one node (CUDA IPC), for the exchange above:
  * alloc returns device memory of `device` and a 64-byte handle to send to the peers; open maps
  * a peer's buffer for access from kernels running on `device` (the ACCESSING device).  Close
@@ -132,6 +166,9 @@ void bspl_function_destroy(bspl_function* fn);
 int bspl_function_info(const bspl_function* fn, int* dtype, int* dim, int* order,
                        int64_t* n_fields, int64_t* n, int* periodic, int* uniform,
                        int64_t* n_knots, double* range_lo, double* range_hi);
+/* CUDA ordinal of the device that holds the function's control points (no reference
+ * counterpart: the reference's splines live in host memory). */
+int bspl_function_device(const bspl_function* fn, int* device);
 /* knots_begin(d)..knots_end(d) (BSpline.hpp:560-571), as double. */
 int bspl_function_knots(const bspl_function* fn, int axis, double* out, int64_t capacity);
 /* spline().control_points() in the plain (non-cell) layout (BSpline.hpp:575-577,
@@ -163,6 +200,15 @@ int bspl_evaluate_value_grad(const bspl_function* fn, int64_t field, const void*
  * operator() where the two disagree): out [n_fields][q]. */
 int bspl_evaluate_fields(const bspl_function* fn, const void* pts, int64_t q, void* out,
                          int on_device, void* stream);
+/* The same with query-major results, out [q][n_fields]: every query's values of all fields side by
+ * side -- what the reference returns for a vector-valued T (one T{...} per query,
+ * interpolation-test.cpp:674-703).  deriv as in bspl_evaluate (NULL: values).  This is the natural
+ * layout of the kernel that serves many fields: queries sorted by cell, one small dense product
+ * (queries of the cell) x (O+1)^D x (fields) per cell, control points read field-minor, whole lines
+ * written per query.  A device `out` should be aligned to 4 elements and n_fields a multiple of 4;
+ * other shapes are served by the field-major kernels plus a transpose. */
+int bspl_evaluate_fields_query_major(const bspl_function* fn, const void* pts, int64_t q,
+                                     const int* deriv, void* out, int on_device, void* stream);
 /* eval_proxy (InterpolationTemplate.hpp:145-176, Interpolation.hpp:493-506): the work that
  * depends only on the query points -- locating them and, on the binned path, sorting them by
  * coefficient tile -- done once and reused for any number of evaluations (any field, any
@@ -178,7 +224,9 @@ int bspl_query_plan_create(const bspl_function* fn, const void* pts, int64_t q, 
 int bspl_template_query_plan_create(const bspl_template* t, const void* pts, int64_t q, int on_device,
                                     void* stream, bspl_query_plan** out);
 /* value_grad == 0: out[q] (deriv == NULL: values); != 0: out[q][1+dim].  Results are in the
- * order of the original points. */
+ * order of the original points.  A device `out` of a value+gradient evaluation through a tiled
+ * (3-D, large-batch) plan must be aligned to 4 elements (32 bytes for fp64): the kernel stores
+ * each result as one vector; any other alignment returns BSPL_ERR_INVALID. */
 int bspl_query_plan_evaluate(const bspl_query_plan* plan, const bspl_function* fn, int64_t field,
                              const int* deriv, int value_grad, void* out, int on_device,
                              void* stream);
@@ -217,6 +265,9 @@ int bspl_host_axis_factor(bspl_dtype dtype, int order, int periodic, int64_t n, 
 
 /* Execution knobs.  path: 0 = auto, 1 = direct gather, 2 = cell-binned tiles. */
 int bspl_set_eval_path(int path);
+/* Many-field evaluation.  path: 0 = auto, 1 = per-query gather out of shared memory (field-major
+ * kernel), 2 = cell-sorted contraction (query-major kernel; field-major results are transposed). */
+int bspl_set_fields_path(int path);
 /* Number of kernels this library launched since the last reset (all threads). */
 int64_t bspl_launch_count(void);
 void bspl_reset_launch_count(void);

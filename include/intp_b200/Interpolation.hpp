@@ -64,10 +64,20 @@ template <typename T> constexpr bspl_dtype dtype_of() {
 //  - vector-valued T (e.g. the reference's Vec<2, float> circle, interpolation-test.cpp:674-703): any
 //    trivially copyable aggregate of K values of U is carried as K fields of one function -- K
 //    independent scalar splines sharing knots, factors and query work.
+// the scalar an aggregate says it is made of (T::value_type), or U when it does not say
+template <typename T, typename U, typename = void>
+struct aggregate_scalar { using type = U; };
+template <typename T, typename U>
+struct aggregate_scalar<T, U, std::void_t<typename T::value_type>> { using type = typename T::value_type; };
 template <typename T, typename U>
 struct components_of {
     static_assert(std::is_arithmetic_v<T> || (std::is_trivially_copyable_v<T> && sizeof(T) % sizeof(U) == 0),
                   "T must be arithmetic or a trivially copyable aggregate of values of the coordinate type U");
+    // Vec<2, float> on the default double coordinates would be reinterpreted as one double: the reference
+    // computes such a T component-wise in T's own arithmetic, here the components must BE coordinates
+    static_assert(std::is_arithmetic_v<T> || std::is_same_v<typename aggregate_scalar<T, U>::type, U>,
+                  "a vector-valued T must consist of values of the coordinate type U "
+                  "(e.g. InterpolationFunction<Vec<2, float>, D, O, float>)");
     static constexpr std::size_t value = std::is_arithmetic_v<T> ? 1 : sizeof(T) / sizeof(U);
 };
 // T is handed to the library as it is

@@ -11,23 +11,27 @@ from oracle.pyoracle import OracleSpline
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("shape", [(34, 29, 41), (34, 30, 48)])
 @pytest.mark.parametrize("order,periodic", [(3, (False, False, False)), (3, (True, False, True)),
                                             (4, (True, True, True)), (2, (False, True, False))])
-def test_staged_solve_single_rank(lib_built, order, periodic):
-    """sweep_axis + function_from_control_points reproduce interpolate() (world size 1)."""
+def test_staged_solve_single_rank(lib_built, order, periodic, shape):
+    """The sharded plan with one rank (bspl_sharded_solve_*: fused first sweep on TMA tiles when the
+    contiguous extent allows it, exchange sweep into its own buffer, last sweep) reproduces
+    interpolate() bit for bit, through both exchanges."""
     import torch
-    from bsplineinterpolation_b200.distributed import ShardedSolve3D
+    from bsplineinterpolation_b200.distributed import ShardedSolve3D, shard_range
     rng = np.random.default_rng(31 + order)
-    shape = (34, 29, 41)
     f = smooth_field(shape, rng)
     ranges = [(0.0, 1.0), (-1.0, 2.0), (0.5, 4.0)]
     sh = ShardedSolve3D(order, shape, ranges, periodic)
+    assert sh.slab0 == [0, shape[0]] and sh.slab1 == [0, shape[1]]
     ctrl = sh.solve(torch.from_numpy(f).cuda())
     o = OracleSpline(order, shape, periodic, lo=[r[0] for r in ranges], hi=[r[1] for r in ranges], f=f)
     assert np.array_equal(ctrl.cpu().numpy(), o.control_points())
     fn = sh.gather_function(ctrl)
     sh.enable_fused_exchange()
     assert np.array_equal(sh.solve_fused(torch.from_numpy(f).cuda()).cpu().numpy(), o.control_points())
+    assert not sh.timed_out()
     sh.close_fused_exchange()
     pts = np.array([r[0] for r in ranges]) + rng.uniform(0, 1, (2000, 3)) * np.array([r[1] - r[0] for r in ranges])
     ref = o.eval(pts)
@@ -58,6 +62,7 @@ def _worker(rank, world, port, out_dir):
         ranges = [(0.0, 1.0)] * 3
         sh = ShardedSolve3D(3, shape, ranges, periodic, device=rank)
         b, e = shard_range(shape[0], rank, world)
+        assert [sh.slab0[rank], sh.slab0[rank + 1]] == [b, e]
         ctrl = sh.solve(torch.from_numpy(f[b:e]).cuda(rank))
         fn = sh.gather_function(ctrl)
         o = OracleSpline(3, shape, periodic, lo=[0, 0, 0], hi=[1, 1, 1], f=f)
@@ -70,7 +75,8 @@ def _worker(rank, world, port, out_dir):
         for _ in range(2):
             fused = sh.solve_fused(torch.from_numpy(f[b:e]).cuda(rank))
             ok = ok and np.array_equal(fused.cpu().numpy(), o.control_points()[:, b1:e1, :])
-        sh.close_fused_exchange()
+        ok = ok and not sh.timed_out()
+        sh.close()
         with open(os.path.join(out_dir, "r%d" % rank), "w") as fh:
             fh.write("%d" % ok)
     finally:

@@ -796,3 +796,155 @@ def test_many_fields_host_path_is_chunked(pkg):
     for k in (0, 299, F - 1):
         single = fn.evaluate(pts, field=k)
         assert np.abs(allv[k] - single).max() <= 1e-13 * np.abs(single).max()
+
+
+# ---- many fields as a per-cell contraction (query-major results) ---------------------------------
+@pytest.mark.parametrize("dim,order,periodic", [(2, 3, (False, False)), (2, 3, (True, False)), (2, 2, (False, True)),
+                                                (2, 5, (True, True)), (2, 1, (False, False)), (2, 4, (False, False)),
+                                                (1, 3, (False,)), (1, 5, (True,)), (3, 1, (False, True, False)),
+                                                (3, 2, (True, False, False)), (3, 3, (False, False, True))])
+def test_many_fields_contraction_query_major(pkg, dim, order, periodic):
+    """bspl_evaluate_fields_query_major: queries sorted by cell, one (queries) x (O+1)^D x (fields) product per
+    cell out of a field-minor copy of the control points.  Equal to per-field evaluation (1e-13) and to the
+    oracle (1e-12); host and device entry points agree."""
+    import torch
+    rng = np.random.default_rng(7000 + 100 * dim + order)
+    shape = {1: (61,), 2: (26, 31), 3: (9, 11, 10)}[dim]
+    F, Q = 72, 30011
+    fields = rng.standard_normal((F,) + shape)
+    lo = [0.0, -1.0, 2.0][:dim]; hi = [1.0, 2.0, 5.0][:dim]
+    fn = pkg.InterpolationFunctionTemplate(order, shape, _ranges(lo, hi), periodic).interpolate(fields)
+    pts = np.array(lo) + rng.uniform(-0.05, 1.05, (Q, dim)) * (np.array(hi) - np.array(lo))
+    pts[:500] = pts[0]        # one crowded cell: more queries than a work item holds
+    dpts = torch.from_numpy(pts).cuda()
+    try:
+        pkg.set_fields_path("contract")
+        qm = fn.evaluate_fields(dpts, layout="query_major").cpu().numpy()
+        host = fn.evaluate_fields(pts, layout="query_major")
+        fm = fn.evaluate_fields(dpts).cpu().numpy()          # field-major through the contraction + transpose
+        dv = [min(order, 1)] + [0] * (dim - 1)
+        dq = fn.evaluate_fields(dpts, layout="query_major", derivatives=dv).cpu().numpy()
+        pkg.set_fields_path("gather")
+        qm_g = fn.evaluate_fields(dpts, layout="query_major").cpu().numpy()   # field-major kernels + transpose
+    finally:
+        pkg.set_fields_path("auto")
+    assert qm.shape == (Q, F) and fm.shape == (F, Q)
+    assert np.array_equal(qm, host)
+    assert np.array_equal(qm.T, fm)
+    inside = np.all((pts >= lo) & (pts <= hi), axis=1) | np.array(periodic).all()
+    for k in (0, 17, F - 1):
+        single = fn.evaluate(pts, field=k)
+        assert np.abs(qm[:, k] - single).max() <= 1e-13 * np.abs(single).max()
+        assert np.abs(qm_g[:, k] - single).max() <= 1e-13 * np.abs(single).max()
+        sd = fn.evaluate(pts, derivatives=dv, field=k)
+        assert np.abs(dq[:, k] - sd).max() <= 1e-12 * max(np.abs(sd).max(), 1e-300)
+        o = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=fields[k])
+        _close(qm[inside, k], o.eval(pts[inside]))
+
+
+def test_many_fields_contraction_odd_shapes_fall_back(pkg):
+    """Field counts the vector accesses cannot serve (not a multiple of 4) and unaligned outputs take the
+    field-major kernels plus a transpose: same numbers."""
+    import torch
+    rng = np.random.default_rng(91)
+    F, shape, Q = 37, (20, 24), 5003
+    fields = rng.standard_normal((F,) + shape)
+    fn = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0), (0.0, 2.0)]).interpolate(fields)
+    pts = rng.uniform(0, 1, (Q, 2)) * np.array([1.0, 2.0])
+    qm = fn.evaluate_fields(torch.from_numpy(pts).cuda(), layout="query_major").cpu().numpy()
+    for k in (0, 36):
+        single = fn.evaluate(pts, field=k)
+        assert np.abs(qm[:, k] - single).max() <= 1e-13 * np.abs(single).max()
+    # re-solving into the same function refreshes the field-minor copy
+    F2 = 64
+    f2 = rng.standard_normal((F2,) + shape)
+    t = pkg.InterpolationFunctionTemplate(3, shape, [(0.0, 1.0), (0.0, 2.0)])
+    fn2 = t.interpolate(f2)
+    a = fn2.evaluate_fields(pts, layout="query_major")
+    t.interpolate(2.0 * f2, into=fn2)
+    b = fn2.evaluate_fields(pts, layout="query_major")
+    assert np.abs(b - 2.0 * a).max() <= 1e-13 * np.abs(b).max()
+
+
+def test_many_fields_contraction_fp32(pkg):
+    rng = np.random.default_rng(92)
+    F, shape, Q = 64, (40, 52), 20000
+    fields = rng.standard_normal((F,) + shape)
+    rg = [(0.0, 1.0), (-1.0, 2.0)]
+    fn32 = pkg.InterpolationFunctionTemplate(3, shape, rg, dtype=np.float32).interpolate(fields.astype(np.float32))
+    fn64 = pkg.InterpolationFunctionTemplate(3, shape, rg).interpolate(fields)
+    pts = np.array([0.0, -1.0]) + rng.uniform(0, 1, (Q, 2)) * np.array([1.0, 3.0])
+    try:
+        pkg.set_fields_path("contract")
+        a = fn32.evaluate_fields(pts.astype(np.float32), layout="query_major")
+    finally:
+        pkg.set_fields_path("auto")
+    assert a.dtype == np.float32 and a.shape == (Q, F)
+    assert rel_err(a, fn64.evaluate_fields(pts, layout="query_major")) <= 1e-5
+
+
+# ---- the binned path's own span selection ---------------------------------------------------------
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("periodic", [(False, False, False), (True, False, True), (False, True, True)])
+def test_binned_path_uses_the_reference_span(pkg, order, periodic):
+    """The O-th derivative of a degree-O spline is constant inside a cell and jumps at every knot, so it tells
+    which span a kernel used.  The cell-binned path has its own locate variants (key_of_point: locate_quick;
+    eval_binned_kernel: locate_uniform_interior / locate): forced on adversarial points (on knots, +-1 ulp
+    around them, range ends, wrapped by whole periods), the top derivative along each axis must be the
+    oracle's -- a span off by one would differ by the size of the jump, not by rounding."""
+    import torch
+    rng = np.random.default_rng(8100 + order)
+    shape = (33, 40, 37)
+    lo, hi = axis_ranges(3, rng)
+    f = rng.standard_normal(shape)          # rough data: neighbouring cells have unrelated top derivatives
+    fn = pkg.InterpolationFunction(order, f, _ranges(lo, hi), periodic)
+    o = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=f)
+    knots = [fn.knots(d) for d in range(3)]
+    rlo = np.array([o.range(d)[0] for d in range(3)]); rhi = np.array([o.range(d)[1] for d in range(3)])
+    pts = np.concatenate([adversarial_points(knots, rlo, rhi, periodic, rng, per_axis=1500),
+                          queries(rlo, rhi, periodic, 20000, rng, mode="wild")])
+    dpts = torch.from_numpy(pts).cuda()
+    spans = o.spans(pts)
+    try:
+        pkg.set_eval_path("binned")
+        assert np.array_equal(fn.locate(pts), spans)
+        for d in range(3):
+            dv = [0, 0, 0]; dv[d] = order
+            got = fn.evaluate(dpts, derivatives=dv).cpu().numpy()
+            ref = o.deriv(pts, dv)
+            jump = np.abs(np.diff(np.unique(np.round(ref, 9)))).min() if len(ref) > 1 else 1.0
+            err = np.abs(got - ref)
+            assert err.max() <= 1e-9 * np.abs(ref).max(), (d, err.max(), np.abs(ref).max(), jump)
+        vg = fn.value_grad(dpts).cpu().numpy()
+        inside = np.all((pts >= rlo) & (pts <= rhi), axis=1) | np.array(periodic).all()
+        _close(vg[inside, 0], o.eval(pts[inside]))
+    finally:
+        pkg.set_eval_path("auto")
+
+
+def test_plan_value_grad_rejects_unaligned_device_output(pkg):
+    """A tiled plan stores {value, gradient} as one 32-byte vector: an unaligned device `out` is refused
+    instead of faulting."""
+    import torch
+    rng = np.random.default_rng(5)
+    shape = (40, 40, 40)
+    fn = pkg.InterpolationFunction(3, rng.standard_normal(shape), [(0.0, 1.0)] * 3)
+    pts = torch.rand((1 << 16, 3), dtype=torch.float64, device="cuda")
+    try:
+        pkg.set_eval_path("binned")
+        plan = fn.eval_proxy(pts)
+        buf = torch.empty((1 << 16) * 4 + 1, dtype=torch.float64, device="cuda")
+        ok = plan(fn, value_grad=True, out=buf[:-1].view(-1, 4))
+        with pytest.raises(pkg.BsplError):
+            plan(fn, value_grad=True, out=buf[1:].view(-1, 4))
+        assert torch.isfinite(ok).all()
+    finally:
+        pkg.set_eval_path("auto")
+
+
+def test_wrong_length_coordinate_arrays_are_refused(pkg):
+    with pytest.raises(ValueError):
+        pkg.InterpolationFunctionTemplate(3, (20, 24), [np.linspace(0, 1, 19), (0.0, 1.0)])
+    # a two-element list on an axis that is not two points long is a (min, max) range
+    t = pkg.InterpolationFunctionTemplate(3, (20, 24), [[0.0, 1.0], [0.0, 2.0]])
+    assert t.shape == (20, 24)
