@@ -411,7 +411,24 @@ def other_configs(B, torch, dev, hbm_peak):
                                             "solve_roofline_frac": sbytes / solve_ms / 1e6 / hbm_peak,
                                             "evaluate_fields_ms": ms, "G_evaluations_per_s": F * Q / ms / 1e6,
                                             "output_stream_frac": F * Q * 8 / ms / 1e6 / hbm_peak}
-        del fn, pts, out, f, t
+        del out
+        torch.cuda.empty_cache()
+        # the same evaluation with query-major results, out[q][field] -- the layout the cell-sorted
+        # contraction produces natively (bspl_evaluate_fields_query_major)
+        try:
+            outT = torch.empty((Q, F), dtype=torch.float64, device=dev)
+            ms2 = timed(lambda: fn.evaluate_fields(pts, out=outT, layout="query_major"), reps=3, warm=1)
+            k = F // 2
+            one = fn.evaluate(pts, field=k)
+            c5 = res["cfg5_4096_fields_128x128"]
+            c5["evaluate_fields_query_major_ms"] = ms2
+            c5["G_evaluations_per_s_query_major"] = F * Q / ms2 / 1e6
+            c5["output_stream_frac_query_major"] = F * Q * 8 / ms2 / 1e6 / hbm_peak
+            c5["max_rel_diff_vs_per_field"] = float((outT[:, k] - one).abs().max().item()) / float(one.abs().max().item())
+            del outT, one
+        except Exception as exc:
+            res["cfg5_4096_fields_128x128"]["query_major_error"] = str(exc)
+        del fn, pts, f, t
     except Exception as exc:
         res["cfg5_4096_fields_128x128"] = {"error": str(exc)}
     torch.cuda.empty_cache()

@@ -108,8 +108,17 @@ struct AxisLU {
     const R* L;       // [n][p]  L(i, i-p+m)
     const R* U;       // [n][q]  U(i, i+1+m)
     const R* diag;    // [n]     U(i, i)
+    const R* rdiag;   // [n]     1 / U(i, i) refined exactly as the fast path of CUDA's IEEE division refines it
+                      //         (fill_refined_reciprocals); fp64 only, nullptr otherwise
     const R* bottom;  // [n][q]  side(n-q+r, j) at [j*q + r]          (cyclic)
     const R* right;   // [n][p]  side(i, n-p+c) at [i*p + c]          (cyclic)
+    // Row-packed copies for the tiled sweeps, which fetch the factor rows of a whole tile with one bulk copy
+    // (launch_pack_factors; n + 32 rows, the padding rows are identity rows):
+    //   fwd_pack[j] = {L(j, .)[p], bottom(., j)[p] if cyclic}          bwd_pack[j] = {U(j, .)[p], right(j, .)[p] if cyclic,
+    //                                                                                  U(j, j), rdiag[j]}
+    // nullptr for compact storage (head < n).
+    const R* fwd_pack;
+    const R* bwd_pack;
     int bottom_len;   // entries j >= bottom_len are exactly zero
     int right_len;    // entries i >= right_len are exactly zero (rows above the main band only)
     int bottom_sig;   // entries j >= bottom_sig are below 1e-30 of the largest (chunked sweeps only)
@@ -143,6 +152,13 @@ struct SweepPlan {
 SweepPlan plan_sweep(int n, long long lines, int window, int cyclic, int bottom_sig);
 template <typename R>
 cudaError_t launch_sweep(const AxisLU<R>& lu, const SweepGeom& g, R* data, const SweepPlan& plan, cudaStream_t s);
+// out[i] = reciprocal of diag[i] for AxisLU::rdiag (device pointers)
+cudaError_t fill_refined_reciprocals(const double* diag, double* out, long long n, cudaStream_t s);
+// AxisLU::fwd_pack / bwd_pack from the row tables of `lu` (device pointers; rows = n + padding)
+template <typename R>
+cudaError_t launch_pack_factors(const AxisLU<R>& lu, long long rows, R* fwd_pack, R* bwd_pack, cudaStream_t s);
+inline int fwd_pack_width(int p, int cyclic) { return (cyclic ? 2 * p : p) > 0 ? (cyclic ? 2 * p : p) : 1; }
+inline int bwd_pack_width(int p, int cyclic) { return (cyclic ? 2 * p : p) + 2; }
 
 // First sweep of the separable solve fused with the copy out of the caller's mesh: lines along
 // the contiguous axis are read from `src` (line space strides src_ms, same extents g.m) and the
