@@ -258,7 +258,16 @@ def sharded_solve_leg(B, torch, dist, local, rank, world, single_ctrl_host):
         full = sh.gather_control_points(run())
         torch.cuda.synchronize()
         if rank == 0 and single_ctrl_host is not None:
-            parity[name] = bool(np.array_equal(full.cpu().numpy(), single_ctrl_host))
+            got = full.cpu().numpy()
+            parity[name] = bool(np.array_equal(got, single_ctrl_host))
+            if not parity[name]:   # where: a diagnosis travels with the line
+                bad = np.argwhere(got != single_ctrl_host)
+                res[name + "_mismatch"] = {"count": int(len(bad)), "first": bad[0].tolist(), "min": bad.min(0).tolist(),
+                                           "max": bad.max(0).tolist(),
+                                           "max_abs": float(np.abs(got - single_ctrl_host).max()),
+                                           "planes0": np.unique(bad[:, 0])[:16].tolist(),
+                                           "rows1": np.unique(bad[:, 1])[:16].tolist()}
+            del got
         del full
         torch.cuda.empty_cache()
     if sh.timed_out():

@@ -7,8 +7,8 @@ from ._capi import BsplError, lib  # noqa: F401
 from .interpolation import (BSpline, InterpolationFunction, InterpolationFunction1D,  # noqa: F401
                             InterpolationFunctionTemplate, InterpolationFunctionTemplate1D,
                             band_solve, band_solve_rows, bspline, last_kernel_ms, launch_count, reset_launch_count,
-                            set_eval_path, set_fields_path)
+                            set_eval_path, set_fields_path, set_sweep_path)
 
 __all__ = ["InterpolationFunction", "InterpolationFunctionTemplate", "InterpolationFunction1D",
            "InterpolationFunctionTemplate1D", "BSpline", "band_solve", "band_solve_rows", "bspline", "lib",
-           "BsplError", "launch_count", "reset_launch_count", "last_kernel_ms", "set_eval_path", "set_fields_path"]
+           "BsplError", "launch_count", "reset_launch_count", "last_kernel_ms", "set_eval_path", "set_fields_path", "set_sweep_path"]

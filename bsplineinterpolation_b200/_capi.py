@@ -65,6 +65,7 @@ SIGNATURES = {
                                         _dp, _dp, _dp, _dp, _dp]),
     "bspl_set_eval_path": (C.c_int, [C.c_int]),
     "bspl_set_fields_path": (C.c_int, [C.c_int]),
+    "bspl_set_sweep_path": (C.c_int, [C.c_int]),
     "bspl_launch_count": (C.c_int64, []),
     "bspl_reset_launch_count": (None, []),
     "bspl_last_kernel_ms": (C.c_double, []),

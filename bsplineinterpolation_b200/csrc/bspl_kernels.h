@@ -243,6 +243,9 @@ struct TransposeGeom {
 template <typename R>
 cudaError_t launch_transpose(const TransposeGeom& g, const R* src, R* dst, cudaStream_t s);
 
+// 0: automatic, 1: thread-per-line sweeps only, 2: the L2-resident tiled sweep whenever TMA can address the lines
+void set_sweep_path(int path);
+
 void count_launch(int n = 1);
 
 }  // namespace bspl

@@ -521,6 +521,12 @@ def last_kernel_ms():
     return lib().bspl_last_kernel_ms()
 
 
+def set_sweep_path(path):
+    """Control-point solve: "auto", "lines" (thread-per-line sweeps only) or "tiled" (the L2-resident TMA
+    sweep wherever it can address the lines); see bspl_set_sweep_path."""
+    check(lib().bspl_set_sweep_path({"auto": 0, "lines": 1, "tiled": 2}.get(path, path)))
+
+
 def set_fields_path(path):
     """Many-field evaluation: "auto", "gather" (per-query gather out of shared memory) or "contract"
     (cell-sorted contraction)."""

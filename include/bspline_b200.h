@@ -268,6 +268,10 @@ int bspl_set_eval_path(int path);
 /* Many-field evaluation.  path: 0 = auto, 1 = per-query gather out of shared memory (field-major
  * kernel), 2 = cell-sorted contraction (query-major kernel; field-major results are transposed). */
 int bspl_set_fields_path(int path);
+/* Control-point solve.  path: 0 = auto, 1 = thread-per-line sweeps only (every line of the mesh in
+ * flight), 2 = the tiled sweep that keeps the lines in flight inside the L2 (one read + one write of
+ * the mesh per axis) wherever TMA can address the lines; auto takes it for meshes larger than the L2. */
+int bspl_set_sweep_path(int path);
 /* Number of kernels this library launched since the last reset (all threads). */
 int64_t bspl_launch_count(void);
 void bspl_reset_launch_count(void);

@@ -11,13 +11,14 @@ from oracle.pyoracle import OracleSpline
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("shape", [(34, 29, 41), (34, 30, 48)])
+@pytest.mark.parametrize("shape", [(34, 29, 41), (34, 30, 48), (40, 136, 64)])
 @pytest.mark.parametrize("order,periodic", [(3, (False, False, False)), (3, (True, False, True)),
                                             (4, (True, True, True)), (2, (False, True, False))])
 def test_staged_solve_single_rank(lib_built, order, periodic, shape):
     """The sharded plan with one rank (bspl_sharded_solve_*: fused first sweep on TMA tiles when the
     contiguous extent allows it, exchange sweep into its own buffer, last sweep) reproduces
-    interpolate() bit for bit, through both exchanges."""
+    interpolate() bit for bit, through both exchanges.  The last shape is long enough along axis 1 for
+    the tiled exchange sweep (sweep_rows_tma_kernel<EXCH>: bulk tensor stores into the owner's buffer)."""
     import torch
     from bsplineinterpolation_b200.distributed import ShardedSolve3D, shard_range
     rng = np.random.default_rng(31 + order)
@@ -56,27 +57,30 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
         rng = np.random.default_rng(5)
-        shape = (50, 37, 44)
-        periodic = (True, False, True)
-        f = smooth_field(shape, rng)
-        ranges = [(0.0, 1.0)] * 3
-        sh = ShardedSolve3D(3, shape, ranges, periodic, device=rank)
-        b, e = shard_range(shape[0], rank, world)
-        assert [sh.slab0[rank], sh.slab0[rank + 1]] == [b, e]
-        ctrl = sh.solve(torch.from_numpy(f[b:e]).cuda(rank))
-        fn = sh.gather_function(ctrl)
-        o = OracleSpline(3, shape, periodic, lo=[0, 0, 0], hi=[1, 1, 1], f=f)
-        ok = np.array_equal(fn.control_points(), o.control_points())
-        back = sh.solve(torch.from_numpy(f[b:e]).cuda(rank), back_to_axis0=True)
-        ok = ok and np.array_equal(back.cpu().numpy(), o.control_points()[b:e])
-        # fused sweep + exchange over peer memory
-        sh.enable_fused_exchange()
-        b1, e1 = shard_range(shape[1], rank, world)
-        for _ in range(2):
-            fused = sh.solve_fused(torch.from_numpy(f[b:e]).cuda(rank))
-            ok = ok and np.array_equal(fused.cpu().numpy(), o.control_points()[:, b1:e1, :])
-        ok = ok and not sh.timed_out()
-        sh.close()
+        ok = True
+        # the second shape is long enough along axis 1 for the tiled exchange sweep; 160 rows over two ranks
+        # put the ownership boundary (row 80) inside a 32-row tile, which is then stored to both owners
+        for shape, periodic in (((50, 37, 44), (True, False, True)), ((66, 160, 96), (False, False, False)),
+                                ((66, 160, 96), (True, True, False))):
+            f = smooth_field(shape, rng)
+            ranges = [(0.0, 1.0)] * 3
+            sh = ShardedSolve3D(3, shape, ranges, periodic, device=rank)
+            b, e = shard_range(shape[0], rank, world)
+            assert [sh.slab0[rank], sh.slab0[rank + 1]] == [b, e]
+            ctrl = sh.solve(torch.from_numpy(f[b:e]).cuda(rank))
+            fn = sh.gather_function(ctrl)
+            o = OracleSpline(3, shape, periodic, lo=[0, 0, 0], hi=[1, 1, 1], f=f)
+            ok = ok and np.array_equal(fn.control_points(), o.control_points())
+            back = sh.solve(torch.from_numpy(f[b:e]).cuda(rank), back_to_axis0=True)
+            ok = ok and np.array_equal(back.cpu().numpy(), o.control_points()[b:e])
+            # fused sweep + exchange over peer memory
+            sh.enable_fused_exchange()
+            b1, e1 = shard_range(shape[1], rank, world)
+            for _ in range(2):
+                fused = sh.solve_fused(torch.from_numpy(f[b:e]).cuda(rank))
+                ok = ok and np.array_equal(fused.cpu().numpy(), o.control_points()[:, b1:e1, :])
+            ok = ok and not sh.timed_out()
+            sh.close()
         with open(os.path.join(out_dir, "r%d" % rank), "w") as fh:
             fh.write("%d" % ok)
     finally:

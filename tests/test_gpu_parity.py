@@ -397,6 +397,41 @@ def test_tma_tiled_contiguous_sweep_bit_exact(pkg, order):
     assert np.abs(fn32.control_points() - ref).max() <= 1e-5 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_l2_resident_tiled_sweeps_bit_exact(pkg, order):
+    """The sweeps that keep their lines in flight inside the L2 (sweep_rows_tma_kernel: TMA row tiles for the
+    strided axes, swizzled boxes for the contiguous axis, packed factor rows staged with the tiles, the
+    division by the pivot taken off the dependent chain) are the automatic choice only for meshes larger than
+    the L2; forced here on small ones: ragged tiles (132 lines = 4.125 warps, 136 = 4.25 tiles of 32 steps),
+    periodic axes (corner strips and tail rows), 2-D, many fields, zeros in the data (operands outside the
+    fast division's range take the full routine) and float.  Control points bit-identical to the oracle's
+    sequential solve in every case."""
+    import torch
+    rng = np.random.default_rng(5200 + order)
+    cases = [((136, 132, 144), [False, False, False]), ((136, 132, 144), [True, True, False]),
+             ((130, 129, 160), [True, False, False]), ((136, 160), [False, False]), ((264, 136), [True, True])]
+    try:
+        pkg.set_sweep_path("tiled")
+        for shape, per in cases:
+            dim = len(shape)
+            fields = 3 if dim == 2 else 1
+            f = rng.standard_normal((fields,) + shape)
+            f[:, 5:9] = 0.0               # exact zeros: right-hand sides the fast division path refuses
+            f[:, -1] = 1e-300
+            t = pkg.InterpolationFunctionTemplate(order, shape, [(0.0, 1.0 + d) for d in range(dim)], per)
+            fn_dev = t.interpolate(torch.from_numpy(f if fields > 1 else f[0]).cuda())
+            for k in range(fields):
+                o = OracleSpline(order, shape, per, lo=[0.0] * dim, hi=[1.0 + d for d in range(dim)], f=f[k])
+                assert np.array_equal(fn_dev.control_points(field=k), o.control_points()), (shape, per, k)
+        f32 = rng.standard_normal((136, 132, 144)).astype(np.float32)
+        fn32 = pkg.InterpolationFunction(order, f32, [(0.0, 1.0)] * 3, dtype=np.float32)
+        pkg.set_sweep_path("lines")
+        ref32 = pkg.InterpolationFunction(order, f32, [(0.0, 1.0)] * 3, dtype=np.float32).control_points()
+        assert np.array_equal(fn32.control_points(), ref32)
+    finally:
+        pkg.set_sweep_path("auto")
+
+
 @pytest.mark.parametrize("order,periodic", [(1, True), (2, False), (3, False), (3, True), (4, True), (5, False), (5, True)])
 def test_chunk_parallel_solve_long_lines(pkg, order, periodic):
     """Few, long lines take the chunk-parallel sweep (warm-up window instead of the sequential
