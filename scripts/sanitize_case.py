@@ -36,5 +36,27 @@ B.InterpolationFunction(3, rng.standard_normal((20000, 40)), [(0.0, 1.0)] * 2, [
 tt = B.InterpolationFunctionTemplate(4, (80, 64, 96), [(0.0, 1.0)] * 3, [True, True, True])
 xx = torch.rand((80, 64, 96), dtype=torch.float64, device="cuda")
 tt.sweep_axis(2, xx, [1, 80, 64], [0, 64 * 96, 96], 1)
+# round 2: the L2-resident tiled sweeps forced on small meshes (strided rows, swizzled contiguous boxes, periodic
+# strips and tail tiles, zeros that send blocks to the full division), the single-rank sharded plan (tiled exchange
+# sweep) and the many-field contraction with query-major results
+B.set_sweep_path("tiled")
+g = rng.standard_normal((136, 132, 144)); g[5:9] = 0.0
+B.InterpolationFunction(3, g, [(0.0, 1.0)] * 3, [False, False, False])
+B.InterpolationFunction(3, g, [(0.0, 1.0)] * 3, [True, True, False])
+B.InterpolationFunction(5, rng.standard_normal((264, 136)), [(0.0, 1.0)] * 2, [True, True])
+B.InterpolationFunction(2, g.astype(np.float32), [(0.0, 1.0)] * 3, dtype=np.float32)
+from bsplineinterpolation_b200.distributed import ShardedSolve3D
+sh = ShardedSolve3D(3, (40, 136, 64), [(0.0, 1.0)] * 3, [True, False, False])
+sh.solve_fused(torch.from_numpy(rng.standard_normal((40, 136, 64))).cuda())
+sh.solve(torch.from_numpy(rng.standard_normal((40, 136, 64))).cuda())
+sh.close()
+B.set_sweep_path("auto")
+t5 = B.InterpolationFunctionTemplate(3, (32, 40), [(0.0, 1.0)] * 2)
+fn5 = t5.interpolate(torch.from_numpy(rng.standard_normal((64, 32, 40))).cuda())
+p5 = torch.from_numpy(rng.uniform(0, 1, (5000, 2))).cuda()
+for path in ("gather", "contract"):
+    B.set_fields_path(path)
+    fn5.evaluate_fields(p5); fn5.evaluate_fields(p5, layout="query_major"); fn5.evaluate_fields(p5, layout="query_major", derivatives=[1, 0])
+B.set_fields_path("auto")
 torch.cuda.synchronize()
 print("sanitize case done")
