@@ -64,6 +64,7 @@ SIGNATURES = {
     "bspl_host_axis_factor": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_double, C.c_double, _dp, _ip,
                                         _dp, _dp, _dp, _dp, _dp]),
     "bspl_set_eval_path": (C.c_int, [C.c_int]),
+    "bspl_template_axis_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "bspl_set_fields_path": (C.c_int, [C.c_int]),
     "bspl_set_sweep_path": (C.c_int, [C.c_int]),
     "bspl_launch_count": (C.c_int64, []),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libbspline_b200.so")
-SOURCES = ["bspl_capi.cu", "bspl_eval.cu", "bspl_solve.cu", "bspl_binned.cu", "bspl_fields.cu", "bspl_contract.cu"]
+SOURCES = ["bspl_capi.cu", "bspl_eval.cu", "bspl_solve.cu", "bspl_binned.cu", "bspl_fields.cu", "bspl_contract.cu", "bspl_factor.cu"]
 HEADERS = ["bspl_device.cuh", "bspl_kernels.h", "bspl_host.h", "bspl_tma.cuh", "../../include/bspline_b200.h"]
 
 NVCC_FLAGS = [

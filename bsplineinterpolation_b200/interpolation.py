@@ -398,6 +398,12 @@ class InterpolationFunctionTemplate:
         evaluates every function this template produces."""
         return QueryPlan(self, points, stream)
 
+    def axis_info(self, axis):
+        """(half bandwidth, cyclic, built on the device) of the solver of one axis; see bspl_template_axis_info."""
+        band, cyc, dev = C.c_int(), C.c_int(), C.c_int()
+        check(lib().bspl_template_axis_info(self._h, int(axis), C.byref(band), C.byref(cyc), C.byref(dev)))
+        return band.value, bool(cyc.value), bool(dev.value)
+
     def sweep_axis(self, axis, data, outer_sizes, outer_strides, line_stride, stream=None):
         """In-place banded/cyclic solve of template axis `axis` along every line of a device
         tensor (one stage of the separable solve); see bspl_template_sweep_axis."""

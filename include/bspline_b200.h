@@ -67,6 +67,11 @@ int bspl_template_create(bspl_dtype dtype, int dim, int order, const int64_t* n,
                          const int* periodic, const double* lo, const double* hi,
                          const double* const* coords, int device, bspl_template** out);
 void bspl_template_destroy(bspl_template* t);
+/* Solver of one axis (solvers_[axis], InterpolationTemplate.hpp:515): half bandwidth p == q
+ * (:291), whether it is the cyclic kind (ExtendedBandMatrix), and whether its collocation matrix
+ * and LU factors were built on the device (long non-uniform, non-periodic axes; everything else
+ * is built on the host, long uniform axes in O(1)).  Any out pointer may be NULL. */
+int bspl_template_axis_info(const bspl_template* t, int axis, int* band, int* cyclic, int* built_on_device);
 
 /* interpolate(mesh) const& (InterpolationTemplate.hpp:118-125) ->
  * solve_for_control_points_ (:448-580) for n_fields meshes stored back to back

@@ -244,6 +244,56 @@ def test_nonuniform_axes_match_oracle(pkg):
             _close(fn.derivative(pts, [1]), o.deriv(pts, [1]))
 
 
+@pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
+def test_long_nonuniform_axis_is_factored_on_the_device(pkg, order, monkeypatch):
+    """collocation matrix and band LU of a long non-uniform, non-periodic axis are built on the
+    device (bspl_factor.cu: one thread per abscissa for the rows, chunk-parallel elimination with a warm-up
+    window, seams checked bit for bit).  The solves must equal the oracle's -- whose LU is the reference's
+    sequential one -- bit for bit: a 1-D axis of 40 000 points, a 2-D mesh with such an axis, and a short axis
+    cut into many small chunks (seams every 64 rows).  Wildly uneven spacing (ratios up to 1e3) is allowed to
+    fail the seam check and fall back to the host; the answer is the same either way."""
+    rng = np.random.default_rng(8300 + order)
+    def coords(n, jitter):
+        x = np.arange(n, dtype=np.float64) + rng.uniform(-jitter, jitter, n)
+        x[0], x[-1] = 0.0, float(n - 1)
+        return np.sort(x) / (n - 1) * 3.0
+    n = 40000
+    xc = coords(n, 0.35)
+    f = rng.standard_normal(n)
+    t = pkg.InterpolationFunctionTemplate(order, (n,), [xc], [False])
+    assert t.axis_info(0) == (order - 1, False, True)
+    o = OracleSpline(order, (n,), [False], coords=[xc], f=f)
+    fn = t.interpolate(f)
+    assert np.array_equal(fn.knots(0), o.knots(0))
+    assert np.array_equal(fn.control_points(), o.control_points())
+    pts = rng.uniform(0, 3, 5000)
+    _close(fn(pts), o.eval(pts))
+    # 2-D, long non-uniform axis first, short uniform periodic axis second
+    shape = (20000, 24)
+    xc2 = coords(shape[0], 0.3)
+    f2 = rng.standard_normal(shape)
+    t2 = pkg.InterpolationFunctionTemplate(order, shape, [xc2, (0.0, 1.0)], [False, True])
+    assert t2.axis_info(0)[2] and not t2.axis_info(1)[2]
+    o2 = OracleSpline(order, shape, [False, True], coords=[xc2, None], lo=[0, 0], hi=[0, 1], f=f2)
+    assert np.array_equal(t2.interpolate(f2).control_points(), o2.control_points())
+    # many seams on a short axis; then spacing so uneven that the device result may be refused
+    monkeypatch.setenv("BSPL_DEVICE_LU_MIN", "200")
+    monkeypatch.setenv("BSPL_DEVICE_LU_CHUNK", "64")
+    monkeypatch.setenv("BSPL_DEVICE_LU_WINDOW", "96")
+    for n3, jitter in ((1500, 0.4), (1500, 0.499)):
+        xc3 = coords(n3, jitter)
+        f3 = rng.standard_normal(n3)
+        t3 = pkg.InterpolationFunctionTemplate(order, (n3,), [xc3], [False])
+        if jitter < 0.45:
+            assert t3.axis_info(0)[2]
+        o3 = OracleSpline(order, (n3,), [False], coords=[xc3], f=f3)
+        assert np.array_equal(t3.interpolate(f3).control_points(), o3.control_points())
+    monkeypatch.setenv("BSPL_DEVICE_LU_MIN", "0")   # disabled: host path
+    t4 = pkg.InterpolationFunctionTemplate(order, (n,), [xc], [False])
+    assert not t4.axis_info(0)[2]
+    assert np.array_equal(t4.interpolate(f).control_points(), o.control_points())
+
+
 def test_template_reuse_many_fields(pkg):
     """InterpolationFunctionTemplate: one mesh, many fields (cfg5 shape, scaled down)."""
     rng = np.random.default_rng(3)
