@@ -22,7 +22,12 @@
 //   on the host instead: the device path is taken only where it provably reproduces the sequential factors
 //   at the seams, and tests/test_gpu_parity.py compares whole solves with the reference's sequential LU.
 //
-// Periodic (cyclic) axes keep the host path: their bordered LU couples the head of the matrix to its last rows.
+// Periodic (cyclic) axes: the band part of the bordered LU (BandLU.hpp:159-213) does not depend on the border at all,
+// and the border -- the two corner strips, which die out geometrically away from the corner, and what they subtract
+// from the P x P corner block -- depends on the first few hundred pivots only.  device_factor (bspl_capi.cu) runs those
+// pivots on the host, on a 4 096-row surrogate assembled from the true axis (BandFactor, bspl_host.h), hands the
+// corrected corner block to the band assembled here, and takes strips and head rows from the host, everything else
+// from the chunked elimination below.
 #include "bspl_kernels.h"
 
 namespace bspl {
@@ -66,15 +71,30 @@ __device__ __forceinline__ void basis_at(const R* __restrict__ t, int O, long lo
     }
 }
 
-// assemble_axis_rows, non-uniform non-periodic branch: band[i][j - i + bw] = A(i, j)
+// assemble_axis_rows, non-uniform branches: band[i][j - i + bw] = A(i, j).  The band is zeroed by the caller.
+// Periodic axes (bordered form, InterpolationTemplate.hpp:383-392): abscissa i fills matrix row i + bw at columns
+// i .. i + cnt - 1; rows and columns that wrap around belong to the corner strips, which the caller builds on the
+// host (device_factor in bspl_capi.cu), and are skipped here.
 template <typename R>
 __global__ void __launch_bounds__(256) assemble_rows_kernel(const R* __restrict__ coords, const R* __restrict__ t, int O,
-                                                            long long n, long long K, int bw, R* __restrict__ band) {
+                                                            long long n, long long K, int bw, int periodic,
+                                                            R* __restrict__ band) {
     const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int w = 2 * bw + 1;
+    R bsv[kFactorMaxOrder + 1];
+    if (periodic) {
+        const long long row0 = i + bw;
+        if (row0 >= n) return;
+        basis_at<R>(t, O, i + O, coords[i], bsv);
+        const int cnt = O | 1;
+        for (int j = 0; j < cnt; ++j) {
+            const long long col = i + j, c = col - row0 + bw;
+            if (col < n && c >= 0 && c < w) band[row0 * w + c] = bsv[j];
+        }
+        return;
+    }
     R* row = band + i * w;
-    for (int c = 0; c < w; ++c) row[c] = R(0);
     if (i == 0 || i == n - 1) {  // end rows interpolate exactly (:317-329)
         row[bw] = R(1);
         return;
@@ -82,7 +102,6 @@ __global__ void __launch_bounds__(256) assemble_rows_kernel(const R* __restrict_
     const R x = coords[i];
     const long long last = (K - O - 1 < i + O) ? K - O - 1 : i + O;
     const long long seg = span_of<R>(t, O, x, i + 1, last);
-    R bsv[kFactorMaxOrder + 1];
     basis_at<R>(t, O, seg, x, bsv);
     const int cnt = O == 1 ? 1 : O + 1;
     const long long col0 = seg - O;
@@ -95,16 +114,16 @@ __global__ void __launch_bounds__(256) assemble_rows_kernel(const R* __restrict_
 // Right-looking band LU of rows [a, b) of chunk c, warmed up from max(0, a - window).  The window of p+1 rows
 // lives in registers: win[r][.] is row k + r of the working matrix while pivot k is processed.
 template <typename R, int P>
-__global__ void __launch_bounds__(128) chunk_lu_kernel(const R* __restrict__ band, long long n, int chunk, int window,
-                                                       long long chunks, R* __restrict__ L, R* __restrict__ U,
-                                                       R* __restrict__ diag, R* __restrict__ check) {
+__global__ void __launch_bounds__(128) chunk_lu_kernel(const R* __restrict__ band, long long n, long long first_row,
+                                                       int chunk, int window, long long chunks, R* __restrict__ L,
+                                                       R* __restrict__ U, R* __restrict__ diag, R* __restrict__ check) {
     using A = Arith<R>;
     constexpr int W = 2 * P + 1;
     constexpr int PP = P > 0 ? P : 1;
     const long long c = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (c >= chunks) return;
-    const long long a = c * chunk, b = (a + chunk < n) ? a + chunk : n;
-    const long long start = a - window > 0 ? a - window : 0;
+    const long long a = first_row + c * chunk, b = (a + chunk < n) ? a + chunk : n;
+    const long long start = a - window > first_row ? a - window : first_row;
     const long long stop = (b + kCheckRows < n) ? b + kCheckRows : n;   // runs into the successor's rows for the seam check
     R win[P + 1][W];
 #pragma unroll
@@ -155,14 +174,15 @@ __global__ void __launch_bounds__(128) chunk_lu_kernel(const R* __restrict__ ban
 template <typename R, int P>
 __global__ void __launch_bounds__(128) check_overlap_kernel(const R* __restrict__ check, const R* __restrict__ L,
                                                             const R* __restrict__ U, const R* __restrict__ diag,
-                                                            long long n, int chunk, long long chunks, int* __restrict__ flag) {
+                                                            long long n, long long first_row, int chunk, long long chunks,
+                                                            int* __restrict__ flag) {
     constexpr int W = 2 * P + 1;
     constexpr int PP = P > 0 ? P : 1;
     const long long v = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (v >= (chunks - 1) * kCheckRows) return;
     const long long c = v / kCheckRows;
     const int e = static_cast<int>(v - c * kCheckRows);
-    const long long k = (c + 1) * chunk + e;
+    const long long k = first_row + (c + 1) * chunk + e;
     if (k >= n) return;
     const R* chk = check + (c * kCheckRows + e) * W;
     bool same = chk[P] == diag[k];
@@ -177,20 +197,31 @@ __global__ void __launch_bounds__(128) check_overlap_kernel(const R* __restrict_
 }  // namespace
 
 template <typename R>
-cudaError_t launch_device_band_factor(int order, long long n, long long K, const R* coords, const R* knots, R* band,
-                                      R* check, R* L, R* U, R* diag, int* flag, int chunk, int window, cudaStream_t s) {
-    const int bw = order - 1;
+cudaError_t launch_device_band_assemble(int order, int periodic, long long n, long long K, const R* coords, const R* knots,
+                                        R* band, cudaStream_t s) {
+    const int bw = periodic ? order / 2 : order - 1;
     if (order < 1 || order > kFactorMaxOrder || n < 2) return cudaErrorInvalidValue;
-    const long long chunks = (n + chunk - 1) / chunk;
+    cudaError_t e = cudaMemsetAsync(band, 0, sizeof(R) * static_cast<size_t>(n) * (2 * bw + 1), s);
+    if (e != cudaSuccess) return e;
+    assemble_rows_kernel<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(coords, knots, order, n, K, bw, periodic, band);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename R>
+cudaError_t launch_device_band_factor(int bw, long long n, long long first_row, const R* band, R* check, R* L, R* U,
+                                      R* diag, int* flag, int chunk, int window, cudaStream_t s) {
+    if (bw < 0 || bw > 4 || n < 2 || first_row < 0 || first_row >= n) return cudaErrorInvalidValue;
+    const long long chunks = (n - first_row + chunk - 1) / chunk;
     cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    assemble_rows_kernel<R><<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(coords, knots, order, n, K, bw, band);
     const unsigned g1 = static_cast<unsigned>((chunks + 127) / 128);
     const unsigned g2 = static_cast<unsigned>(((chunks - 1) * kCheckRows + 127) / 128);
-#define BSPL_LU_CASE(P_)                                                                                          \
-    case P_:                                                                                                      \
-        chunk_lu_kernel<R, P_><<<g1, 128, 0, s>>>(band, n, chunk, window, chunks, L, U, diag, check);              \
-        if (chunks > 1) check_overlap_kernel<R, P_><<<g2, 128, 0, s>>>(check, L, U, diag, n, chunk, chunks, flag); \
+#define BSPL_LU_CASE(P_)                                                                                                \
+    case P_:                                                                                                            \
+        chunk_lu_kernel<R, P_><<<g1, 128, 0, s>>>(band, n, first_row, chunk, window, chunks, L, U, diag, check);         \
+        if (chunks > 1)                                                                                                 \
+            check_overlap_kernel<R, P_><<<g2, 128, 0, s>>>(check, L, U, diag, n, first_row, chunk, chunks, flag);        \
         break;
     switch (bw) {
         BSPL_LU_CASE(0)
@@ -201,18 +232,22 @@ cudaError_t launch_device_band_factor(int order, long long n, long long K, const
         default: return cudaErrorInvalidValue;
     }
 #undef BSPL_LU_CASE
-    count_launch(chunks > 1 ? 3 : 2);
+    count_launch(chunks > 1 ? 2 : 1);
     return cudaGetLastError();
 }
 
-size_t device_band_factor_check_elems(long long n, int order, int chunk) {
+size_t device_band_factor_check_elems(long long n, int bw, int chunk) {
     const long long chunks = (n + chunk - 1) / chunk;
-    return static_cast<size_t>(chunks) * kCheckRows * (2 * (order - 1) + 1);
+    return static_cast<size_t>(chunks) * kCheckRows * (2 * bw + 1);
 }
 
-template cudaError_t launch_device_band_factor<double>(int, long long, long long, const double*, const double*, double*,
-                                                       double*, double*, double*, double*, int*, int, int, cudaStream_t);
-template cudaError_t launch_device_band_factor<float>(int, long long, long long, const float*, const float*, float*, float*,
-                                                      float*, float*, float*, int*, int, int, cudaStream_t);
+template cudaError_t launch_device_band_assemble<double>(int, int, long long, long long, const double*, const double*, double*,
+                                                         cudaStream_t);
+template cudaError_t launch_device_band_assemble<float>(int, int, long long, long long, const float*, const float*, float*,
+                                                        cudaStream_t);
+template cudaError_t launch_device_band_factor<double>(int, long long, long long, const double*, double*, double*, double*,
+                                                       double*, int*, int, int, cudaStream_t);
+template cudaError_t launch_device_band_factor<float>(int, long long, long long, const float*, float*, float*, float*, float*,
+                                                      int*, int, int, cudaStream_t);
 
 }  // namespace bspl

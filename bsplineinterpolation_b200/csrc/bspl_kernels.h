@@ -157,14 +157,18 @@ cudaError_t fill_refined_reciprocals(const double* diag, double* out, long long 
 // AxisLU::fwd_pack / bwd_pack from the row tables of `lu` (device pointers; rows = n + padding)
 template <typename R>
 cudaError_t launch_pack_factors(const AxisLU<R>& lu, long long rows, R* fwd_pack, R* bwd_pack, cudaStream_t s);
-// Collocation rows + band LU of a long non-uniform, non-periodic axis on the device (bspl_factor.cu).  coords[n],
-// knots[K]: device; band [n][2(order-1)+1] and check [device_band_factor_check_elems] are scratch; L, U [n][max(p,1)]
-// and diag [n] receive the factors in AxisLU's row form; *flag != 0 afterwards: the chunks did not agree bit for bit
-// at their seams -- discard the result.
+// Collocation rows + band LU of a long non-uniform axis on the device (bspl_factor.cu).  assemble: coords, knots
+// device arrays -> band [n][2 bw + 1] (bw = order-1, or order/2 on a periodic axis, whose wrapping entries are left
+// out).  factor: band -> L, U [n][max(bw,1)], diag [n] in AxisLU's row form for rows >= first_row (warm-ups never
+// reach below it); check [device_band_factor_check_elems] is scratch; *flag != 0 afterwards: the chunks did not
+// agree bit for bit at their seams -- discard the result.
 template <typename R>
-cudaError_t launch_device_band_factor(int order, long long n, long long K, const R* coords, const R* knots, R* band,
-                                      R* check, R* L, R* U, R* diag, int* flag, int chunk, int window, cudaStream_t s);
-size_t device_band_factor_check_elems(long long n, int order, int chunk);
+cudaError_t launch_device_band_assemble(int order, int periodic, long long n, long long K, const R* coords, const R* knots,
+                                        R* band, cudaStream_t s);
+template <typename R>
+cudaError_t launch_device_band_factor(int bw, long long n, long long first_row, const R* band, R* check, R* L, R* U,
+                                      R* diag, int* flag, int chunk, int window, cudaStream_t s);
+size_t device_band_factor_check_elems(long long n, int bw, int chunk);
 inline int fwd_pack_width(int p, int cyclic) { return (cyclic ? 2 * p : p) > 0 ? (cyclic ? 2 * p : p) : 1; }
 inline int bwd_pack_width(int p, int cyclic) { return (cyclic ? 2 * p : p) + 2; }
 

@@ -246,9 +246,10 @@ def test_nonuniform_axes_match_oracle(pkg):
 
 @pytest.mark.parametrize("order", [1, 2, 3, 4, 5])
 def test_long_nonuniform_axis_is_factored_on_the_device(pkg, order, monkeypatch):
-    """collocation matrix and band LU of a long non-uniform, non-periodic axis are built on the
+    """collocation matrix and band LU of a long non-uniform axis are built on the
     device (bspl_factor.cu: one thread per abscissa for the rows, chunk-parallel elimination with a warm-up
-    window, seams checked bit for bit).  The solves must equal the oracle's -- whose LU is the reference's
+    window, seams checked bit for bit; periodic axes too, with the border of their bordered LU taken from a
+    host surrogate of the first pivots).  The solves must equal the oracle's -- whose LU is the reference's
     sequential one -- bit for bit: a 1-D axis of 40 000 points, a 2-D mesh with such an axis, and a short axis
     cut into many small chunks (seams every 64 rows).  Wildly uneven spacing (ratios up to 1e3) is allowed to
     fail the seam check and fall back to the host; the answer is the same either way."""
@@ -292,6 +293,23 @@ def test_long_nonuniform_axis_is_factored_on_the_device(pkg, order, monkeypatch)
     t4 = pkg.InterpolationFunctionTemplate(order, (n,), [xc], [False])
     assert not t4.axis_info(0)[2]
     assert np.array_equal(t4.interpolate(f).control_points(), o.control_points())
+    monkeypatch.delenv("BSPL_DEVICE_LU_MIN"); monkeypatch.delenv("BSPL_DEVICE_LU_CHUNK"); monkeypatch.delenv("BSPL_DEVICE_LU_WINDOW")
+    # periodic: the border of the bordered LU (corner strips, corner block) comes from the host, the band from the device
+    if order >= 2:
+        xp = coords(n + 1, 0.35)
+        tp = pkg.InterpolationFunctionTemplate(order, (n,), [xp], [True])
+        assert tp.axis_info(0) == (order // 2, True, True)
+        op = OracleSpline(order, (n,), [True], coords=[xp], f=f)
+        fp = tp.interpolate(f)
+        assert np.array_equal(fp.knots(0), op.knots(0))
+        assert np.array_equal(fp.control_points(), op.control_points())
+        shape = (24, 20000)
+        xp2 = coords(shape[1] + 1, 0.3)
+        f2p = rng.standard_normal(shape)
+        t2p = pkg.InterpolationFunctionTemplate(order, shape, [(0.0, 1.0), xp2], [False, True])
+        assert t2p.axis_info(1)[2]
+        o2p = OracleSpline(order, shape, [False, True], coords=[None, xp2], lo=[0, 0], hi=[1, 0], f=f2p)
+        assert np.array_equal(t2p.interpolate(f2p).control_points(), o2p.control_points())
 
 
 def test_template_reuse_many_fields(pkg):
