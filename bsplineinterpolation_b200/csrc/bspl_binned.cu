@@ -471,7 +471,7 @@ BinnedScratch binned_scratch_view(void* base, long long q, int max_tiles) {
 
 template <typename R>
 int binned_tile_count(const EvalArgs<R>& a) {
-    if (a.dim != 3) return 0;
+    if (a.dim != 3 || a.order > 5) return 0;
     const int T = tile_edge_rt(a.order);
     long long n = 1;
     for (int d = 0; d < 3; ++d) n *= (a.ax[d].K - 2 * a.order - 1 + T - 1) / T;

@@ -338,6 +338,7 @@ FieldsScratch fields_scratch_view(void* base, long long q, int n_keys, int K, si
 }
 
 bool fields_contract_supported(int dim, int order) {
+    if (dim > 3 || order > 5) return false;   // the sort and weight kernels are instantiated for those
     int K = 1;
     for (int d = 0; d < dim; ++d) K *= order + 1;
     switch (K) {

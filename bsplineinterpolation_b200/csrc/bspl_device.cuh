@@ -9,8 +9,8 @@
 
 namespace bspl {
 
-constexpr int kMaxDim = 3;
-constexpr int kMaxOrder = 5;
+constexpr int kMaxDim = 4;
+constexpr int kMaxOrder = 7;
 
 // Per-axis description handed to kernels by value.
 template <typename R>

@@ -125,6 +125,100 @@ __global__ void __launch_bounds__(256) eval_direct_kernel(const EvalKernelParams
     }
 }
 
+// Any dimension up to kMaxDim and any order up to kMaxOrder with run-time loops: the route for 4-D splines and
+// for orders 6 and 7, which the reference's templates accept (Interpolation.hpp:17) but the unrolled kernel above is
+// not instantiated for.  The stencil is walked with an odometer over the slower axes, the fastest axis contracted
+// first; the gradient substitutes the derivative weights one axis at a time.
+template <typename R, int O, bool GRAD>
+__global__ void __launch_bounds__(128) eval_generic_kernel(const EvalKernelParams<R, kMaxDim> p, int dim) {
+    constexpr int W = O + 1;
+    const int nout = GRAD ? dim + 1 : 1;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < p.q; q += stride) {
+        R w[kMaxDim][W], dw[GRAD ? kMaxDim : 1][W];
+        long long base = 0;
+        for (int d = 0; d < dim; ++d) {
+            const R x = p.pts[q * dim + d];
+            base += axis_setup<R, O, GRAD>(p.ax[d], x, GRAD ? 0 : p.deriv[d], w[d], dw[GRAD ? d : 0]);
+        }
+        int outer = 1;
+        for (int d = 0; d + 1 < dim; ++d) outer *= W;
+        for (int f = 0; f < p.n_fields; ++f) {
+            const R* c = p.coef + f * p.field_stride + base;
+            // nested sums, as the unrolled kernels form them: part[s][d] collects, for result s (0: value, 1 + e:
+            // derivative along axis e), the terms of the current run of axis d; when axis d + 1 completes a cycle its
+            // sum is folded into axis d with that axis' weight.  Rounding error grows with (O + 1) * dim, not (O + 1)^dim.
+            R part[GRAD ? kMaxDim + 1 : 1][kMaxDim];
+#pragma unroll
+            for (int r = 0; r < (GRAD ? kMaxDim + 1 : 1); ++r)
+#pragma unroll
+                for (int d = 0; d < kMaxDim; ++d) part[r][d] = R(0);
+            R v = R(0), g[kMaxDim] = {R(0), R(0), R(0), R(0)};
+            for (int t = 0; t < outer; ++t) {
+                int idx[kMaxDim] = {0, 0, 0, 0};
+                long long off = 0;
+                int rem = t;
+                for (int d = dim - 2; d >= 0; --d) {
+                    idx[d] = rem % W; rem /= W;
+                    off += idx[d] * p.ax[d].stride;
+                }
+                R a = R(0), a1 = R(0);
+#pragma unroll
+                for (int k = 0; k < W; ++k) {
+                    const R cv = c[off + k];
+                    a += cv * w[dim - 1][k];
+                    if (GRAD) a1 += cv * dw[GRAD ? dim - 1 : 0][k];
+                }
+                if (dim == 1) {
+                    v = a;
+                    if (GRAD) g[0] = a1;
+                    break;
+                }
+                // fold the finished innermost sum into axis dim-2, then carry upwards wherever a cycle completed
+                const int lastd = dim - 2;
+                part[0][lastd] += a * w[lastd][idx[lastd]];
+                if (GRAD) {
+                    for (int e = 0; e < dim; ++e) {
+                        const R src = (e == dim - 1) ? a1 : a;
+                        const R wt = (e == lastd) ? dw[GRAD ? lastd : 0][idx[lastd]] : w[lastd][idx[lastd]];
+                        part[GRAD ? 1 + e : 0][lastd] += src * wt;
+                    }
+                }
+                for (int d = lastd; d >= 1 && idx[d] == W - 1; --d) {
+                    part[0][d - 1] += part[0][d] * w[d - 1][idx[d - 1]];
+                    part[0][d] = R(0);
+                    if (GRAD) {
+                        for (int e = 0; e < dim; ++e) {
+                            const R wt = (e == d - 1) ? dw[GRAD ? d - 1 : 0][idx[d - 1]] : w[d - 1][idx[d - 1]];
+                            part[GRAD ? 1 + e : 0][d - 1] += part[GRAD ? 1 + e : 0][d] * wt;
+                            part[GRAD ? 1 + e : 0][d] = R(0);
+                        }
+                    }
+                }
+            }
+            if (dim > 1) {
+                v = part[0][0];
+                if (GRAD)
+                    for (int e = 0; e < dim; ++e) g[e] = part[GRAD ? 1 + e : 0][0];
+            }
+            R* o = p.out + (static_cast<long long>(f) * p.q + q) * nout;
+            o[0] = v;
+            if (GRAD)
+                for (int e = 0; e < dim; ++e) o[1 + e] = g[e];
+        }
+    }
+}
+
+template <typename R, int O>
+__global__ void __launch_bounds__(256) locate_generic_kernel(const EvalKernelParams<R, kMaxDim> p, int dim, int32_t* cell) {
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < p.q; q += stride)
+        for (int d = 0; d < dim; ++d) {
+            R x = p.pts[q * dim + d];
+            cell[q * dim + d] = locate<R, O>(p.ax[d], x) - O;
+        }
+}
+
 template <typename R, int D, int O>
 __global__ void __launch_bounds__(256) locate_kernel(const EvalKernelParams<R, D> p, int32_t* cell) {
     const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
@@ -200,9 +294,52 @@ cudaError_t locate_DO(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s) {
 
 }  // namespace
 
+template <typename R, int O>
+cudaError_t eval_generic_O(const EvalArgs<R>& a, cudaStream_t s) {
+    EvalKernelParams<R, kMaxDim> p{};
+    for (int d = 0; d < a.dim; ++d) { p.ax[d] = a.ax[d]; p.deriv[d] = a.deriv[d]; }
+    p.coef = a.coef; p.field_stride = a.field_stride; p.n_fields = a.n_fields;
+    p.pts = a.pts; p.out = a.out; p.q = a.q;
+    const int block = 128;
+    const int grid = grid_for(a.q, block, kSMs * 32);
+    if (a.mode == kValueGrad) eval_generic_kernel<R, O, true><<<grid, block, 0, s>>>(p, a.dim);
+    else eval_generic_kernel<R, O, false><<<grid, block, 0, s>>>(p, a.dim);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <typename R, int O>
+cudaError_t locate_generic_O(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s) {
+    EvalKernelParams<R, kMaxDim> p{};
+    for (int d = 0; d < a.dim; ++d) p.ax[d] = a.ax[d];
+    p.pts = a.pts; p.q = a.q;
+    locate_generic_kernel<R, O><<<grid_for(a.q, 256, kSMs * 32), 256, 0, s>>>(p, a.dim, cell);
+    count_launch();
+    return cudaGetLastError();
+}
+
+#define BSPL_DISPATCH_GENERIC(CALL)                                    \
+    switch (a.order) {                                                 \
+        case 0: return CALL(0);                                        \
+        case 1: return CALL(1);                                        \
+        case 2: return CALL(2);                                        \
+        case 3: return CALL(3);                                        \
+        case 4: return CALL(4);                                        \
+        case 5: return CALL(5);                                        \
+        case 6: return CALL(6);                                        \
+        case 7: return CALL(7);                                        \
+        default: return cudaErrorInvalidValue;                         \
+    }
+
 template <typename R>
 cudaError_t launch_eval_direct(const EvalArgs<R>& a, cudaStream_t s) {
     if (a.q <= 0) return cudaSuccess;
+    if (a.dim < 1 || a.dim > kMaxDim) return cudaErrorInvalidValue;
+    if (a.dim > 3 || a.order > 5) {
+#define CALL_GEN(O_) eval_generic_O<R, O_>(a, s)
+        BSPL_DISPATCH_GENERIC(CALL_GEN)
+#undef CALL_GEN
+    }
 #define CALL_EVAL(D_, O_) eval_direct_DO<R, D_, O_>(a, s)
     BSPL_DISPATCH(CALL_EVAL)
 #undef CALL_EVAL
@@ -211,6 +348,12 @@ cudaError_t launch_eval_direct(const EvalArgs<R>& a, cudaStream_t s) {
 template <typename R>
 cudaError_t launch_locate(const EvalArgs<R>& a, int32_t* cell, cudaStream_t s) {
     if (a.q <= 0) return cudaSuccess;
+    if (a.dim < 1 || a.dim > kMaxDim) return cudaErrorInvalidValue;
+    if (a.dim > 3 || a.order > 5) {
+#define CALL_GLOC(O_) locate_generic_O<R, O_>(a, cell, s)
+        BSPL_DISPATCH_GENERIC(CALL_GLOC)
+#undef CALL_GLOC
+    }
 #define CALL_LOC(D_, O_) locate_DO<R, D_, O_>(a, cell, s)
     BSPL_DISPATCH(CALL_LOC)
 #undef CALL_LOC

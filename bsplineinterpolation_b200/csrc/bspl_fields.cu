@@ -205,7 +205,7 @@ cudaError_t fields_O(const EvalArgs<R>& a, cudaStream_t s) {
 template <typename R>
 bool fields_smem_eligible(const EvalArgs<R>& a) {
     const long long bytes = a.field_stride * static_cast<long long>(sizeof(R));
-    return a.dim == 2 && a.mode == kValue && a.n_fields >= 8 && a.q >= 4096 && bytes % 16 == 0 &&
+    return a.dim == 2 && a.order <= 5 && a.mode == kValue && a.n_fields >= 8 && a.q >= 4096 && bytes % 16 == 0 &&
            bytes <= 192 * 1024 && a.field_stride <= 65535;  // + 31 KB of stage and slot table; 16-bit element offsets
 }
 

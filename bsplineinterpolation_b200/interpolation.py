@@ -111,12 +111,12 @@ class InterpolationFunction:
         L = lib()
         dt, dim, order = C.c_int(), C.c_int(), C.c_int()
         nf = C.c_int64()
-        n = (C.c_int64 * 3)()
-        per = (C.c_int * 3)()
-        uni = (C.c_int * 3)()
-        nk = (C.c_int64 * 3)()
-        lo = (C.c_double * 3)()
-        hi = (C.c_double * 3)()
+        n = (C.c_int64 * 8)()
+        per = (C.c_int * 8)()
+        uni = (C.c_int * 8)()
+        nk = (C.c_int64 * 8)()
+        lo = (C.c_double * 8)()
+        hi = (C.c_double * 8)()
         check(L.bspl_function_info(self._h, dt, dim, order, nf, n, per, uni, nk, lo, hi))
         self.dtype = _NP[dt.value]
         self.dim, self.order, self.n_fields = dim.value, order.value, nf.value

@@ -32,8 +32,8 @@
 extern "C" {
 #endif
 
-#define BSPL_MAX_DIM 3
-#define BSPL_MAX_ORDER 5
+#define BSPL_MAX_DIM 4
+#define BSPL_MAX_ORDER 7
 
 typedef enum {
     BSPL_OK = 0,

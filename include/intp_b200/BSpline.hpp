@@ -28,7 +28,7 @@ namespace intp {
 
 template <typename T, std::size_t D, std::size_t O, typename U = double>
 class BSpline {
-    static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..3, order 0..5");
+    static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..4, order 0..7 (the reference takes any; these are the instantiated device kernels)");
     static_assert(std::is_same_v<T, U> && (std::is_same_v<T, double> || std::is_same_v<T, float>),
                   "BSpline: T and U must both be double or both be float");
 

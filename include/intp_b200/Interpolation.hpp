@@ -235,7 +235,7 @@ class EvalProxy {
 // ---------------------------------------------------------------- InterpolationFunction
 template <typename T, std::size_t D, std::size_t O, typename U = double>
 class InterpolationFunction {
-    static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..3, order 0..5");
+    static_assert(D >= 1 && D <= BSPL_MAX_DIM && O <= BSPL_MAX_ORDER, "dim 1..4, order 0..7 (the reference takes any; these are the instantiated device kernels)");
 
    public:
     using val_type = T;

@@ -182,6 +182,8 @@ RefBase* make_order(int order, const size_t* n, const AxisSpec* ax, const double
         case 3: return new Ref<D, 3>(n, ax, f, rep);
         case 4: return new Ref<D, 4>(n, ax, f, rep);
         case 5: return new Ref<D, 5>(n, ax, f, rep);
+        case 6: return new Ref<D, 6>(n, ax, f, rep);
+        case 7: return new Ref<D, 7>(n, ax, f, rep);
         default: return nullptr;
     }
 }
@@ -208,8 +210,9 @@ SHIM_API void* intp_ref_create(int dim, int order, const uint64_t* n, const int*
                                const double* const* coords, const uint64_t* n_coords,
                                const double* f, int repeat) {
     try {
-        AxisSpec ax[3];
-        size_t nn[3];
+        AxisSpec ax[4];
+        size_t nn[4];
+        if (dim < 1 || dim > 4) return nullptr;
         for (int d = 0; d < dim; ++d) {
             nn[d] = size_t(n[d]);
             ax[d] = AxisSpec{periodic[d], lo[d], hi[d],
@@ -220,6 +223,7 @@ SHIM_API void* intp_ref_create(int dim, int order, const uint64_t* n, const int*
             case 1: return make_order<1>(order, nn, ax, f, repeat);
             case 2: return make_order<2>(order, nn, ax, f, repeat);
             case 3: return make_order<3>(order, nn, ax, f, repeat);
+            case 4: return make_order<4>(order, nn, ax, f, repeat);
             default: return nullptr;
         }
     } catch (const std::exception&) {

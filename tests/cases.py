@@ -52,7 +52,7 @@ def adversarial_points(knots, lo, hi, periodic, rng, per_axis=400):
 
 
 def small_shapes(dim, order, periodic):
-    base = {1: (37,), 2: (19, 23), 3: (11, 9, 13)}[dim]
+    base = {1: (37,), 2: (19, 23), 3: (11, 9, 13), 4: (8, 7, 9, 10)}[dim]
     return tuple(max(n, order + 2) for n in base)
 
 
@@ -61,6 +61,18 @@ def all_combos(dims=(1, 2, 3), orders=range(6)):
         for order in orders:
             for per in itertools.product([False, True], repeat=dim):
                 yield dim, order, per
+
+
+def extended_combos():
+    """(dim, order, periodic) beyond the everyday set: orders 6 and 7 in 1-3 dimensions, and 4-D splines -- what the
+    reference's templates accept (Interpolation.hpp:17) and this build serves with its generic kernels."""
+    for dim in (1, 2, 3):
+        for order in (6, 7):
+            for per in ([False] * dim, [True] * dim, [d % 2 == 0 for d in range(dim)]):
+                yield dim, order, tuple(per)
+    for order in (1, 2, 3, 5, 6):
+        for per in ((False, False, False, False), (True, False, True, False), (True, True, True, True)):
+            yield 4, order, per
 
 
 def long_axis_field(n):

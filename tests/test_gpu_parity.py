@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import rel_err
-from cases import adversarial_points, all_combos, axis_ranges, queries, small_shapes, smooth_field
+from cases import adversarial_points, all_combos, axis_ranges, extended_combos, queries, small_shapes, smooth_field
 from oracle.pyoracle import OracleSpline
 
 pytestmark = pytest.mark.gpu
@@ -72,6 +72,54 @@ def test_solve_and_eval_match_oracle(pkg, dim, order, periodic):
     for d in range(dim):
         dv = [0] * dim; dv[d] = 1
         _close(vg[:, 1 + d], o.deriv(pts, dv))
+
+
+@pytest.mark.parametrize("dim,order,periodic", sorted(set(extended_combos())))
+def test_extended_dims_and_orders_match_oracle(pkg, dim, order, periodic):
+    """What the reference's templates accept beyond the everyday set (Interpolation.hpp:17 takes any D and Order):
+    orders 6 and 7 -- half bandwidth 5 and 6 on non-periodic axes -- and 4-D splines, served by the run-time-loop
+    kernels (eval_generic_kernel, the thread-per-line sweep for wide bands, one sweep launch per field in 4-D).
+    Control points and spans bit-identical to the oracle (pinned against the reference on these very
+    combinations, tests/test_oracle.py); values / derivatives / gradient to 1e-12 of the magnitude of the terms
+    summed: on these tiny high-order meshes the control points reach 10^3 - 10^4 times the field (the collocation
+    problem is that ill-conditioned), so the bar is 1e-12 * max|control point| / max|field| relative."""
+    rng = np.random.default_rng(7000 + 100 * dim + 10 * order + sum(periodic))
+    shape = small_shapes(dim, order, periodic)
+    lo, hi = axis_ranges(dim, rng)
+    f = smooth_field(shape, rng)
+    o = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=f)
+    fn = pkg.InterpolationFunction(order, f, _ranges(lo, hi), periodic)
+    for d in range(dim):
+        assert np.array_equal(fn.knots(d), o.knots(d))
+        assert fn.range(d) == o.range(d)
+    assert np.array_equal(fn.control_points(), o.control_points())
+    tol = 1e-12 * max(1.0, np.abs(o.control_points()).max() / np.abs(f).max())
+    rlo = np.array([o.range(d)[0] for d in range(dim)]); rhi = np.array([o.range(d)[1] for d in range(dim)])
+    adv = adversarial_points([o.knots(d) for d in range(dim)], rlo, rhi, periodic, rng)
+    assert np.array_equal(fn.locate(adv), o.spans(adv))
+    pts = queries(rlo, rhi, periodic, 2000, rng)
+    assert np.array_equal(fn.locate(pts), o.spans(pts))
+    _close(fn(pts), o.eval(pts), tol)
+    for dv in ([1] + [0] * (dim - 1), [min(order, 2)] * dim, [0] * (dim - 1) + [order]):
+        _close(fn.derivative(pts, dv), o.deriv(pts, dv), tol)
+    assert not fn.derivative(pts, [order + 1] + [0] * (dim - 1)).any()
+    vg = fn.value_grad(pts)
+    _close(vg[:, 0], o.eval(pts), tol)
+    for d in range(dim):
+        dv = [0] * dim; dv[d] = 1
+        _close(vg[:, 1 + d], o.deriv(pts, dv), tol)
+    # two fields on one template, device pointers, and the many-field entry points (fallback routes here)
+    import torch
+    f2 = np.stack([f, smooth_field(shape, rng)])
+    t = pkg.InterpolationFunctionTemplate(order, shape, _ranges(lo, hi), periodic)
+    fn2 = t.interpolate(torch.from_numpy(f2).cuda())
+    o2 = OracleSpline(order, shape, periodic, lo=lo, hi=hi, f=f2[1])
+    assert np.array_equal(fn2.control_points(field=1), o2.control_points())
+    dp = torch.from_numpy(pts).cuda()
+    both = fn2.evaluate_fields(dp).cpu().numpy()
+    _close(both[0], o.eval(pts), tol); _close(both[1], o2.eval(pts), 10 * tol)
+    qm = fn2.evaluate_fields(dp, layout="query_major").cpu().numpy()
+    _close(qm[:, 1], o2.eval(pts), 10 * tol)
 
 
 def test_reference_golden_vectors(pkg, golden):

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import ROOT, rel_err
-from cases import adversarial_points, all_combos, axis_ranges, queries, small_shapes, smooth_field
+from cases import adversarial_points, all_combos, axis_ranges, extended_combos, queries, small_shapes, smooth_field
 from oracle import pyoracle
 from oracle.pyoracle import OracleSpline
 
@@ -138,7 +138,7 @@ needs_ref = pytest.mark.skipif(not pyoracle.ref_available(), reason="oracle/_ref
 
 
 @needs_ref
-@pytest.mark.parametrize("dim,order,periodic", list(all_combos()))
+@pytest.mark.parametrize("dim,order,periodic", list(all_combos()) + sorted(set(extended_combos())))
 def test_port_equals_reference(dim, order, periodic):
     """knots, ranges, spans and control points bit-identical; values/derivatives <= 1e-13."""
     from oracle.pyoracle import RefSpline
