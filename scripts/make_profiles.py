@@ -55,11 +55,12 @@ for rep in ("%s_eval_pipeline" % tag, "%s_solve" % tag):
                 return x * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}.get(un, 1)
             traffic[name.split("(")[0].split("::")[-1].split("<")[0]] = val('dram__bytes_read.sum') + val('dram__bytes_write.sum')
     print(open(os.path.join(P, rep + "_summary.txt")).read())
-q = 67108864
+q = 1 << int(os.environ.get("PROFILE_LOG2_Q", "28"))
 ev = sum(traffic.get(k, 0) for k in ("eval_binned_kernel", "scatter_kernel", "key_count_kernel"))
-json.dump({"eval_bytes_per_query": ev / q if ev else None, "queries_in_capture": q,
+commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+json.dump({"eval_bytes_per_query": ev / q if ev else None, "queries_in_capture": q, "commit": commit, "round": tag,
            "kernels": {k: v for k, v in traffic.items()},
            "note": "dram__bytes_read.sum + dram__bytes_write.sum of key_count + scatter + eval_binned, one launch each, "
-                   "ncu --set full, 2^26 queries, 256^3 cubic fp64 value+gradient"},
+                   "ncu --set full --clock-control none, %d queries, 256^3 cubic fp64 value+gradient; solve kernels: 512^3" % q},
           open(os.path.join(P, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(P, "traffic.json")).read())
