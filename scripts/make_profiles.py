@@ -24,6 +24,23 @@ with open(os.path.join(P, "%s_launch_shares.txt" % tag), "w") as fh:
     fh.write("kernel, launches, total_ms, share_of_our_kernels\n")
     for k, (n, v) in sorted(mine.items(), key=lambda kv: -kv[1][1]):
         fh.write("%s, %d, %.3f, %.1f%%\n" % (k, n, v / 1e6, 100 * v / s))
+# the device-resident steps alone (warm-up + timed: everything up to the 5th full-size evaluation kernel); the rest of
+# the list is the end-to-end leg's 2^22-query chunks, whose kernels have other proportions
+big, seen = {}, 0
+for _, k, v in launches:
+    name = k.split("(")[0].split("::")[-1]
+    if not any(t in name for t in ("key_count", "tile_totals", "plan_kernel", "key_cursor", "scatter_kernel", "eval_binned")):
+        continue
+    big.setdefault(name, [0, 0.0]); big[name][0] += 1; big[name][1] += v
+    if "eval_binned" in name:
+        seen += 1
+        if seen == 5:
+            break
+with open(os.path.join(P, "%s_launch_shares.txt" % tag), "a") as fh:
+    s5 = sum(v[1] for v in big.values())
+    fh.write("\n# device-resident steps only (first 5 evaluate calls of 2^28 queries): kernel, launches, ms per step, share of the step\n")
+    for k, (n, v) in sorted(big.items(), key=lambda kv: -kv[1][1]):
+        fh.write("%s, %d, %.3f, %.1f%%\n" % (k, n, v / 1e6 / 5, 100 * v / s5))
 print(open(os.path.join(P, "%s_launch_shares.txt" % tag)).read())
 
 # 2. full-set summaries
@@ -36,14 +53,18 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.avg']
 traffic = {}
-for rep in ("%s_eval_pipeline" % tag, "%s_solve" % tag):
+for rep in ("%s_eval_pipeline" % tag, "%s_solve" % tag, "%s_fields_contract" % tag):
     path = os.path.join(G, rep + ".ncu-rep")
-    if not os.path.exists(path):
+    raw = os.path.join(G, rep + ".raw.csv")   # exported on the GPU box when the report itself is too large to bring back
+    if os.path.exists(raw):
+        out = open(raw).read()
+    elif os.path.exists(path):
+        out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    else:
         continue
-    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rr = list(csv.reader(out.splitlines())); h, u = rr[0], rr[1]
     with open(os.path.join(P, rep + "_summary.txt"), "w") as fh:
-        fh.write("# ncu --set full --clock-control none --import-source on (one launch each)\n")
+        fh.write("# ncu --set full --clock-control none (one launch each; raw page exported on the GPU box)\n")
         for r in rr[2:]:
             name = r[h.index('Kernel Name')]
             fh.write("== %s\n" % name)
