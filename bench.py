@@ -276,7 +276,8 @@ def sharded_solve_leg(B, torch, dist, local, rank, world, single_ctrl_host):
     res["parity_detail"] = parity
     res["parity_against"] = "control points of the single-GPU solve on rank 0, numpy.array_equal (bit-identical)"
     sbytes = 2 * 8 * 3 * float(np.prod(SOLVE_MESH))
-    res["algorithmic_gbs_aggregate"] = sbytes / min(res["nccl_ms"], res["fused_ms"]) / 1e6
+    res["best_ms"] = min(res["nccl_ms"], res["fused_ms"])
+    res["algorithmic_gbs_aggregate"] = sbytes / res["best_ms"] / 1e6
     sh.close()
     del f
     torch.cuda.empty_cache()
@@ -659,12 +660,16 @@ def run_gpu(args):
             fields_sharded = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
     if rank == 0:
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("eval_bytes_per_query")
+                tj = json.load(open(tp))
+                traffic = tj.get("eval_bytes_per_query")
                 traffic = traffic * q if traffic is not None else None
+                traffic_src = ("ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of key_count + scatter + eval_binned, "
+                               "%d queries, commit %s (profiles/traffic.json), scaled to this run's query count"
+                               % (tj.get("queries_in_capture", 0), tj.get("commit", "?")))
             except Exception:
                 traffic = None
         line = {
@@ -677,7 +682,7 @@ def run_gpu(args):
                        "l2": "inputs+outputs (%.1f GB per step) exceed the 126 MB L2" % (q * B_STREAM / 1e9),
                        "strong": strong},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": traffic, "peak_kind": peak_kind,
+                         "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_kind": peak_kind,
                          "kernel_ms": kern_ms, "kernel": "whole evaluate call (key_count, scans, scatter, eval_binned)",
                          "dominant_kernel": dominant, "bytes_per_query": B_QUERY,
                          "stream_only_frac": q * B_STREAM / (kern_ms * 1e-3) / 1e9 / hbm_peak,
